@@ -1,0 +1,295 @@
+// fp.cuh - 254-bit prime-field arithmetic for BN254 (Fq base field, Fr scalar field) on sm_100a.
+//
+// Replaces, on the device, what ark-ff 0.5.0's Fp256<MontBackend> (+asm, /root/reference/Cargo.toml:25) does on the
+// CPU for the prover hot path.  Representation: 8 x 32-bit limbs, little-endian, Montgomery form with R = 2^256 -
+// bit-identical in memory to the 4 x u64 LE Montgomery words the zkey stores (/root/reference/src/zkey.rs:327-332),
+// so proving-key sections are uploaded without any conversion.
+//
+// The Montgomery product is a CIOS loop on two half-width accumulators ("even"/"odd" columns) so that every
+// 32x32->64 partial product is one mad.lo.cc/madc.hi.cc pair (one IMAD.WIDE after ptxas) and every carry chain lives
+// inside a single asm block.  All results are fully reduced to [0, p).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2g {
+
+struct alignas(32) fe { uint32_t l[8]; };
+
+// ---------------------------------------------------------------------------------------------- moduli
+struct FqParams {
+    // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    static constexpr uint32_t P0 = 0xd87cfd47u, P1 = 0x3c208c16u, P2 = 0x6871ca8du, P3 = 0x97816a91u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t INV = 0xe4866389u;              // -q^-1 mod 2^32
+    // R mod q (Montgomery one)
+    static constexpr uint32_t R0 = 0xc58f0d9du, R1 = 0xd35d438du, R2 = 0xf5c70b3du, R3 = 0x0a78eb28u,
+                              R4 = 0x7879462cu, R5 = 0x666ea36fu, R6 = 0x9a07df2fu, R7 = 0x0e0a77c1u;
+    // R^2 mod q
+    static constexpr uint32_t RR0 = 0x538afa89u, RR1 = 0xf32cfc5bu, RR2 = 0xd44501fbu, RR3 = 0xb5e71911u,
+                              RR4 = 0x0a417ff6u, RR5 = 0x47ab1effu, RR6 = 0xcab8351fu, RR7 = 0x06d89f71u;
+};
+struct FrParams {
+    // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+    static constexpr uint32_t P0 = 0xf0000001u, P1 = 0x43e1f593u, P2 = 0x79b97091u, P3 = 0x2833e848u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t INV = 0xefffffffu;
+    static constexpr uint32_t R0 = 0x4ffffffbu, R1 = 0xac96341cu, R2 = 0x9f60cd29u, R3 = 0x36fc7695u,
+                              R4 = 0x7879462eu, R5 = 0x666ea36fu, R6 = 0x9a07df2fu, R7 = 0x0e0a77c1u;
+    static constexpr uint32_t RR0 = 0xae216da7u, RR1 = 0x1bb8e645u, RR2 = 0xe35c59e3u, RR3 = 0x53fe3ab1u,
+                              RR4 = 0x53bb8085u, RR5 = 0x8c49833du, RR6 = 0x7f4e44a5u, RR7 = 0x0216d0b1u;
+};
+
+// ---------------------------------------------------------------------------------------------- raw helpers
+__device__ __forceinline__ bool fe_is_zero(const fe& a) {
+    return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0u;
+}
+__device__ __forceinline__ bool fe_equal(const fe& a, const fe& b) {
+    return ((a.l[0] ^ b.l[0]) | (a.l[1] ^ b.l[1]) | (a.l[2] ^ b.l[2]) | (a.l[3] ^ b.l[3]) |
+            (a.l[4] ^ b.l[4]) | (a.l[5] ^ b.l[5]) | (a.l[6] ^ b.l[6]) | (a.l[7] ^ b.l[7])) == 0u;
+}
+__device__ __forceinline__ fe fe_zero() {
+    fe r;
+    r.l[0] = 0; r.l[1] = 0; r.l[2] = 0; r.l[3] = 0; r.l[4] = 0; r.l[5] = 0; r.l[6] = 0; r.l[7] = 0;
+    return r;
+}
+
+// 256-bit loads/stores of one element (32-byte aligned)
+__device__ __forceinline__ fe fe_load(const void* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    fe r; r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ fe fe_load_nc(const void* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    fe r; r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void fe_store(void* p, const fe& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// ---------------------------------------------------------------------------------------------- the field
+template <class P>
+struct Fp {
+    using elem = fe;
+
+    static __device__ __forceinline__ fe zero() { return fe_zero(); }
+    static __device__ __forceinline__ fe one() {
+        fe r; r.l[0] = P::R0; r.l[1] = P::R1; r.l[2] = P::R2; r.l[3] = P::R3; r.l[4] = P::R4; r.l[5] = P::R5; r.l[6] = P::R6; r.l[7] = P::R7;
+        return r;
+    }
+    static __device__ __forceinline__ fe r2() {
+        fe r; r.l[0] = P::RR0; r.l[1] = P::RR1; r.l[2] = P::RR2; r.l[3] = P::RR3; r.l[4] = P::RR4; r.l[5] = P::RR5; r.l[6] = P::RR6; r.l[7] = P::RR7;
+        return r;
+    }
+    static __device__ __forceinline__ bool is_zero(const fe& a) { return fe_is_zero(a); }
+    static __device__ __forceinline__ bool eq(const fe& a, const fe& b) { return fe_equal(a, b); }
+
+    // r = a - p if a >= p else a     (a < 2p)
+    static __device__ __forceinline__ fe reduce_once(const fe& a) {
+        fe t; uint32_t br;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7]), "=r"(br)
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "n"(P::P0), "n"(P::P1), "n"(P::P2), "n"(P::P3), "n"(P::P4), "n"(P::P5), "n"(P::P6), "n"(P::P7));
+        fe r;
+        #pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = br ? a.l[i] : t.l[i];
+        return r;
+    }
+
+    static __device__ __forceinline__ fe add(const fe& a, const fe& b) {
+        fe s;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s.l[0]), "=r"(s.l[1]), "=r"(s.l[2]), "=r"(s.l[3]), "=r"(s.l[4]), "=r"(s.l[5]), "=r"(s.l[6]), "=r"(s.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+        return reduce_once(s);      // a, b < p < 2^254  =>  no carry out of limb 7
+    }
+    static __device__ __forceinline__ fe dbl(const fe& a) { return add(a, a); }
+
+    static __device__ __forceinline__ fe sub(const fe& a, const fe& b) {
+        fe d; uint32_t br;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(d.l[0]), "=r"(d.l[1]), "=r"(d.l[2]), "=r"(d.l[3]), "=r"(d.l[4]), "=r"(d.l[5]), "=r"(d.l[6]), "=r"(d.l[7]), "=r"(br)
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+        // br = 0xffffffff when a < b: add p back
+        uint32_t m0 = P::P0 & br, m1 = P::P1 & br, m2 = P::P2 & br, m3 = P::P3 & br,
+                 m4 = P::P4 & br, m5 = P::P5 & br, m6 = P::P6 & br, m7 = P::P7 & br;
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(d.l[0]), "+r"(d.l[1]), "+r"(d.l[2]), "+r"(d.l[3]), "+r"(d.l[4]), "+r"(d.l[5]), "+r"(d.l[6]), "+r"(d.l[7])
+            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(m6), "r"(m7));
+        return d;
+    }
+    static __device__ __forceinline__ fe neg(const fe& a) { return sub(zero(), a); }
+
+    // ------------------------------------------------------------------ Montgomery product
+    // acc[0..7] = { lo,hi of x0*b ; x1*b ; x2*b ; x3*b }
+    static __device__ __forceinline__ void mul4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+        asm("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t"
+            "mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
+            "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t"
+            "mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;"
+            : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
+            : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    }
+    // acc += { x0*b ; x1*b ; x2*b ; x3*b } as one 256-bit carry chain; the carry out is added to `top`
+    static __device__ __forceinline__ void cmad4(uint32_t* acc, uint32_t& top, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+        asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %2;\n\t madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %4;\n\t madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, %6;\n\t madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+            "addc.u32 %8, %8, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(top)
+            : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    }
+    // same, carry out discarded (provably zero)
+    static __device__ __forceinline__ void cmad4_nc(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+        asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9, %12, %2;\n\t madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+            "madc.lo.cc.u32 %4, %10, %12, %4;\n\t madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t madc.hi.u32 %7, %11, %12, %7;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+            : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    }
+    // x0 += e[1] (carry into the chain);  e[j], e[j+1] = {x_odd * b} + e[j+2], e[j+3]  (in-place two-limb right shift)
+    static __device__ __forceinline__ void madc_shift(uint32_t& x0, uint32_t* e, uint32_t a1, uint32_t a3, uint32_t a5, uint32_t a7, uint32_t b) {
+        asm("add.cc.u32 %8, %8, %1;\n\t"
+            "madc.lo.cc.u32 %0, %9, %13, %2;\n\t madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
+            "madc.lo.cc.u32 %2, %10, %13, %4;\n\t madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
+            "madc.lo.cc.u32 %4, %11, %13, %6;\n\t madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
+            "madc.lo.cc.u32 %6, %12, %13, 0;\n\t madc.hi.u32 %7, %12, %13, 0;"
+            : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(x0)
+            : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
+    }
+
+    // one CIOS row: x = array aligned to limb 0, e = array that becomes the limb-1-aligned one
+    static __device__ __forceinline__ void row(uint32_t* x, uint32_t* e, const fe& a, uint32_t b, bool first) {
+        if (first) {
+            mul4(e, a.l[1], a.l[3], a.l[5], a.l[7], b);
+            mul4(x, a.l[0], a.l[2], a.l[4], a.l[6], b);
+        } else {
+            madc_shift(x[0], e, a.l[1], a.l[3], a.l[5], a.l[7], b);
+            cmad4(x, e[7], a.l[0], a.l[2], a.l[4], a.l[6], b);
+        }
+        uint32_t m = x[0] * P::INV;
+        cmad4_nc(e, P::P1, P::P3, P::P5, P::P7, m);
+        cmad4(x, e[7], P::P0, P::P2, P::P4, P::P6, m);
+    }
+
+    static __device__ __forceinline__ fe mul(const fe& a, const fe& b) {
+        uint32_t ev[8], od[8];
+        row(ev, od, a, b.l[0], true);
+        row(od, ev, a, b.l[1], false);
+        row(ev, od, a, b.l[2], false);
+        row(od, ev, a, b.l[3], false);
+        row(ev, od, a, b.l[4], false);
+        row(od, ev, a, b.l[5], false);
+        row(ev, od, a, b.l[6], false);
+        row(od, ev, a, b.l[7], false);
+        // after the last row: od is limb-0 aligned with od[0] == 0, ev is limb-1 aligned; result = ev + (od >> 32)
+        fe r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, 0;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+              "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+        return reduce_once(r);
+    }
+    static __device__ __forceinline__ fe sqr(const fe& a) { return mul(a, a); }
+
+    static __device__ __forceinline__ fe from_canonical(const fe& a) { return mul(a, r2()); }
+    static __device__ __forceinline__ fe to_canonical(const fe& a) {
+        fe o = fe_zero(); o.l[0] = 1; return mul(a, o);
+    }
+
+    // a^(p-2); not on any per-element hot path (3 per proof + key precomputation)
+    static __device__ __noinline__ fe inv(const fe& a) {
+        const uint32_t e[8] = {P::P0 - 2u, P::P1, P::P2, P::P3, P::P4, P::P5, P::P6, P::P7};
+        fe acc = one();
+        for (int i = 255; i >= 0; i--) {
+            acc = sqr(acc);
+            if ((e[i >> 5] >> (i & 31)) & 1u) acc = mul(acc, a);
+        }
+        return acc;
+    }
+};
+
+using Fq = Fp<FqParams>;
+using Fr = Fp<FrParams>;
+
+// ---------------------------------------------------------------------------------------------- Fq2 = Fq[u]/(u^2+1)
+struct fe2 { fe c0, c1; };
+
+struct Fq2 {
+    using elem = fe2;
+    static __device__ __forceinline__ fe2 zero() { fe2 r; r.c0 = fe_zero(); r.c1 = fe_zero(); return r; }
+    static __device__ __forceinline__ fe2 one() { fe2 r; r.c0 = Fq::one(); r.c1 = fe_zero(); return r; }
+    static __device__ __forceinline__ bool is_zero(const fe2& a) { return fe_is_zero(a.c0) && fe_is_zero(a.c1); }
+    static __device__ __forceinline__ bool eq(const fe2& a, const fe2& b) { return fe_equal(a.c0, b.c0) && fe_equal(a.c1, b.c1); }
+    static __device__ __forceinline__ fe2 add(const fe2& a, const fe2& b) { fe2 r; r.c0 = Fq::add(a.c0, b.c0); r.c1 = Fq::add(a.c1, b.c1); return r; }
+    static __device__ __forceinline__ fe2 sub(const fe2& a, const fe2& b) { fe2 r; r.c0 = Fq::sub(a.c0, b.c0); r.c1 = Fq::sub(a.c1, b.c1); return r; }
+    static __device__ __forceinline__ fe2 dbl(const fe2& a) { fe2 r; r.c0 = Fq::dbl(a.c0); r.c1 = Fq::dbl(a.c1); return r; }
+    static __device__ __forceinline__ fe2 neg(const fe2& a) { fe2 r; r.c0 = Fq::neg(a.c0); r.c1 = Fq::neg(a.c1); return r; }
+    static __device__ __noinline__ fe2 mul(const fe2& a, const fe2& b) {
+        fe v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
+        fe s = Fq::add(a.c0, a.c1), t = Fq::add(b.c0, b.c1);
+        fe m = Fq::mul(s, t);
+        fe2 r; r.c0 = Fq::sub(v0, v1); r.c1 = Fq::sub(Fq::sub(m, v0), v1);
+        return r;
+    }
+    static __device__ __noinline__ fe2 sqr(const fe2& a) {
+        fe s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
+        fe2 r; r.c0 = Fq::mul(s, d); r.c1 = Fq::dbl(m);
+        return r;
+    }
+    static __device__ __noinline__ fe2 inv(const fe2& a) {
+        fe d = Fq::inv(Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1)));
+        fe2 r; r.c0 = Fq::mul(a.c0, d); r.c1 = Fq::neg(Fq::mul(a.c1, d));
+        return r;
+    }
+};
+
+}  // namespace b2g

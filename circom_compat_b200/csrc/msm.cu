@@ -1,0 +1,345 @@
+// msm.cu - kernels and launchers of the fixed-base-table Pippenger MSM described in msm.cuh.
+#include "msm.cuh"
+#include "util.cuh"
+
+namespace b2g {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+// ------------------------------------------------------------------------------------------------ key-load time
+// T[w][i] = 2^(c*w) * P_i, affine.  One thread per base; the nwin XYZZ multiples live in local memory and are brought
+// back to affine with one field inversion per thread (Montgomery's trick over ZZZ).
+template <class C, class F>
+__global__ void __launch_bounds__(128) msm_table_kernel(const void* __restrict__ bases, uint32_t n, int c, int nwin, void* __restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    using Pt = typename C::Pt; using Aff = typename C::Aff; using E = typename F::elem;
+    Aff p = aff_load<F>(bases, i);
+    if (C::aff_is_inf(p)) {
+        Aff z; z.x = F::zero(); z.y = F::zero();
+        for (int w = 0; w < nwin; w++) aff_store<F>(table, (size_t)w * n + i, z);
+        return;
+    }
+    Pt pts[MSM_MAX_WIN];
+    E pre[MSM_MAX_WIN];
+    Pt cur = C::from_affine(p);
+    E acc = F::one();
+    for (int w = 0; w < nwin; w++) {
+        pts[w] = cur;
+        pre[w] = acc;
+        acc = F::mul(acc, cur.zzz);                 // never zero: prime-order group, P != inf
+        if (w + 1 < nwin) for (int j = 0; j < c; j++) cur = C::dbl(cur);
+    }
+    E inv = F::inv(acc);
+    for (int w = nwin - 1; w >= 0; w--) {
+        E iz = F::mul(inv, pre[w]);                 // 1/zzz_w
+        inv = F::mul(inv, pts[w].zzz);
+        Aff a;
+        a.y = F::mul(pts[w].y, iz);
+        a.x = F::mul(pts[w].x, F::mul(F::sqr(pts[w].zz), F::sqr(iz)));
+        aff_store<F>(table, (size_t)w * n + i, a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (1) digits + histogram
+__global__ void __launch_bounds__(256) msm_count_kernel(const fe* __restrict__ scalars, uint32_t n, int scalars_mont, int c, int nwin,
+                                 fe* __restrict__ canon_out, uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe k = fe_load_nc(&scalars[i]);
+    if (scalars_mont) k = Fr::to_canonical(k);
+    fe_store(&canon_out[i], k);
+    if (fe_is_zero(k)) return;
+    uint32_t carry = 0;
+    for (int w = 0; w < nwin; w++) {
+        int32_t d = msm_digit(k.l, c, w, carry);
+        if (d != 0) atomicAdd(&counts[(d < 0 ? -d : d) - 1], 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (2) exclusive scan (one CTA)
+__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ offsets,
+                                                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ big_count) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const uint32_t tid = threadIdx.x, per = (nb + 1023u) / 1024u;
+    const uint32_t lo = tid * per, hi = min(lo + per, nb);
+    uint32_t s = 0;
+    for (uint32_t j = lo; j < hi; j++) s += counts[j];
+    // block exclusive scan of s
+    uint32_t v = s;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if ((tid & 31) >= (uint32_t)d) v += t; }
+    if ((tid & 31) == 31) warp_sums[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t w = warp_sums[tid], x = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, x, d); if (tid >= (uint32_t)d) x += t; }
+        warp_sums[tid] = x - w;
+        if (tid == 31) carry_s = x;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[tid >> 5] + v - s;
+    for (uint32_t j = lo; j < hi; j++) { offsets[j] = run; cursor[j] = 0; run += counts[j]; }
+    if (tid == 0) { offsets[nb] = carry_s; *big_count = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------ (3) scatter
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const fe* __restrict__ canon, uint32_t n, uint32_t row_stride, int c, int nwin, const uint32_t* __restrict__ offsets,
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe k = fe_load_nc(&canon[i]);
+    if (fe_is_zero(k)) return;
+    uint32_t carry = 0;
+    for (int w = 0; w < nwin; w++) {
+        int32_t d = msm_digit(k.l, c, w, carry);
+        if (d != 0) {
+            uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
+            uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
+            entries[pos] = ((uint32_t)w * row_stride + i) | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (4) accumulate
+// Thread t owns sorted positions [t*chunk, (t+1)*chunk).  Buckets that lie entirely inside the run are written to
+// buckets[]; a run's first / last segment that belongs to a bucket crossing the run boundary goes to frag_first[t] /
+// frag_last[t].
+template <class C, class F>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
+                                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
+                                      void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last) {
+    using Pt = typename C::Pt; using Aff = typename C::Aff;
+    const uint32_t total = offsets[nb];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t start64 = (uint64_t)t * chunk;
+    if (start64 >= total) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (uint32_t)min((uint64_t)total, start64 + chunk);
+    // bucket containing `start`: largest b with offsets[b] <= start (and non-empty by construction of the search)
+    uint32_t lo = 0, hi = nb;                       // invariant: offsets[lo] <= start < offsets[hi]
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= start) lo = mid; else hi = mid; }
+    uint32_t b = lo;
+    uint32_t bucket_end = offsets[b + 1];
+    while (bucket_end <= start) { b++; bucket_end = offsets[b + 1]; }    // skip empty buckets sharing the offset
+    Pt acc = C::infinity();
+    uint32_t seg_start = start;
+    for (uint32_t pos = start; pos < end;) {
+        uint32_t e = entries[pos];
+        Aff p = aff_load<F>(table, (size_t)(e & 0x7fffffffu));
+        if (e >> 31) p.y = F::neg(p.y);
+        C::madd(acc, p);
+        pos++;
+        if (pos == bucket_end || pos == end) {
+            const uint32_t bucket_start = offsets[b];
+            if (bucket_start >= start && bucket_end <= end) pt_store<F>(buckets, b, acc);
+            else if (seg_start == start) pt_store<F>(frag_first, t, acc);
+            else pt_store<F>(frag_last, t, acc);
+            acc = C::infinity();
+            seg_start = pos;
+            if (pos == bucket_end && pos < end) {
+                do { b++; bucket_end = offsets[b + 1]; } while (bucket_end <= pos);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (5) fold fragments
+template <class C, class F>
+__global__ void __launch_bounds__(128) msm_fold_kernel(const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk, void* __restrict__ buckets,
+                                const void* __restrict__ frag_first, const void* __restrict__ frag_last,
+                                uint32_t* __restrict__ big_list, uint32_t* __restrict__ big_count) {
+    using Pt = typename C::Pt;
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t s = offsets[b], e = offsets[b + 1];
+    if (s == e) { pt_store<F>(buckets, b, C::infinity()); return; }
+    uint32_t t0 = s / chunk, t1 = (e - 1) / chunk;
+    if (t0 == t1) return;                                   // complete bucket, already written by (4)
+    if (t1 - t0 + 1 > (uint32_t)MSM_BIG_FRAGS) { big_list[atomicAdd(big_count, 1u)] = b; return; }
+    Pt acc = (s == t0 * chunk) ? pt_load<F>(frag_first, t0) : pt_load<F>(frag_last, t0);
+    for (uint32_t t = t0 + 1; t <= t1; t++) { Pt q = pt_load<F>(frag_first, t); C::add(acc, q); }
+    pt_store<F>(buckets, b, acc);
+}
+
+// shared-memory tree sum of one point per thread; result valid in thread 0
+template <class C, class F, int NT>
+__device__ __forceinline__ typename C::Pt block_sum_points(typename C::Pt v, typename C::Pt* sh) {
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    #pragma unroll 1
+    for (int d = NT / 2; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) { typename C::Pt a = sh[threadIdx.x]; typename C::Pt q = sh[threadIdx.x + d]; C::add(a, q); sh[threadIdx.x] = a; }
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+constexpr int MSM_TREE_THREADS = 128;
+
+// buckets with many fragments: one CTA each
+template <class C, class F>
+__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_fold_big_kernel(const uint32_t* __restrict__ offsets, uint32_t chunk, void* __restrict__ buckets,
+                                    const void* __restrict__ frag_first, const void* __restrict__ frag_last,
+                                    const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count) {
+    using Pt = typename C::Pt;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    Pt* sh = reinterpret_cast<Pt*>(smem_raw);
+    const uint32_t nbig = *big_count;
+    for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+        uint32_t b = big_list[bi];
+        uint32_t s = offsets[b], e = offsets[b + 1];
+        uint32_t t0 = s / chunk, t1 = (e - 1) / chunk;
+        Pt acc = C::infinity();
+        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += MSM_TREE_THREADS) {
+            Pt q = (t == t0 && s != t0 * chunk) ? pt_load<F>(frag_last, t0) : pt_load<F>(frag_first, t);
+            C::add(acc, q);
+        }
+        Pt r = block_sum_points<C, F, MSM_TREE_THREADS>(acc, sh);
+        if (threadIdx.x == 0) pt_store<F>(buckets, b, r);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (6) weighted bucket sum
+// sum_b (b+1) * B_b.  Thread t takes buckets [t*S, (t+1)*S): running sums give A_t = sum_j (j+1) B_{tS+j} and
+// S_t = sum_j B_{tS+j}; its contribution is A_t + (t*S) * S_t (small double-and-add); a CTA tree adds them up.
+template <class C, class F>
+__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_reduce_kernel(const void* __restrict__ buckets, uint32_t nb, void* __restrict__ partials) {
+    using Pt = typename C::Pt;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    Pt* sh = reinterpret_cast<Pt*>(smem_raw);
+    const uint32_t t = blockIdx.x * MSM_TREE_THREADS + threadIdx.x;
+    const uint32_t base = t * MSM_REDUCE_CHUNK;
+    Pt run = C::infinity(), acc = C::infinity();
+    if (base < nb) {
+        const uint32_t cnt = min((uint32_t)MSM_REDUCE_CHUNK, nb - base);
+        for (int j = (int)cnt - 1; j >= 0; j--) {
+            Pt q = pt_load<F>(buckets, base + j);
+            C::add(run, q);
+            C::add(acc, run);
+        }
+        // acc += base * run
+        if (base != 0 && !C::is_inf(run)) {
+            Pt m = C::infinity();
+            int top = 31 - __clz(base);
+            for (int i = top; i >= 0; i--) { m = C::dbl(m); if ((base >> i) & 1u) C::add(m, run); }
+            C::add(acc, m);
+        }
+    }
+    Pt r = block_sum_points<C, F, MSM_TREE_THREADS>(acc, sh);
+    if (threadIdx.x == 0) pt_store<F>(partials, blockIdx.x, r);
+}
+
+// sum of `count` points (count <= a few hundred) by one CTA
+template <class C, class F>
+__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_sum_kernel(const void* __restrict__ pts, uint32_t count, void* __restrict__ out) {
+    using Pt = typename C::Pt;
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    Pt* sh = reinterpret_cast<Pt*>(smem_raw);
+    Pt acc = C::infinity();
+    for (uint32_t i = threadIdx.x; i < count; i += MSM_TREE_THREADS) { Pt q = pt_load<F>(pts, i); C::add(acc, q); }
+    Pt r = block_sum_points<C, F, MSM_TREE_THREADS>(acc, sh);
+    if (threadIdx.x == 0) pt_store<F>(out, 0, r);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <class C, class F>
+static void msm_build_table_t(MsmPlan& plan, const void* bases_dev, uint32_t n, cudaStream_t st) {
+    const size_t aff = 2 * Bytes<F>::ELEM;
+    plan.n = n; plan.c = msm_pick_c(n ? n : 1); plan.nwin = msm_nwin(plan.c); plan.nbuckets = 1u << (plan.c - 1);
+    if (n == 0) { plan.table = nullptr; return; }
+    if ((uint64_t)n * plan.nwin >= (1ull << 31)) throw_error(B2G_E_SHAPE, "msm: n * windows exceeds 2^31 table rows");
+    CUDA_CHECK(cudaMalloc(&plan.table, (size_t)n * plan.nwin * aff));
+    msm_table_kernel<C, F><<<(n + 127) / 128, 128, 0, st>>>(bases_dev, n, plan.c, plan.nwin, plan.table);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void msm_build_table(MsmPlan& plan, const void* bases_dev, uint32_t n, bool g2, cudaStream_t st) {
+    plan.g2 = g2;
+    if (g2) msm_build_table_t<G2, Fq2>(plan, bases_dev, n, st);
+    else msm_build_table_t<G1, Fq>(plan, bases_dev, n, st);
+}
+
+void msm_free_table(MsmPlan& plan) { if (plan.table) cudaFree(plan.table); plan.table = nullptr; }
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    long x = strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t)x : dflt;
+}
+
+void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2) {
+    s.g2 = g2; s.cap_n = n; s.cap_nwin = nwin; s.cap_buckets = nbuckets;
+    s.chunk = env_u32("B2G_MSM_CHUNK", 64);
+    const size_t pt = (g2 ? 4 * 64 : 4 * 32);
+    const size_t nent = (size_t)n * nwin;
+    const size_t nchunks = (nent + s.chunk - 1) / s.chunk + 1;
+    const size_t nred = ((size_t)nbuckets + MSM_REDUCE_CHUNK - 1) / MSM_REDUCE_CHUNK;
+    const size_t npart = (nred + MSM_TREE_THREADS - 1) / MSM_TREE_THREADS;
+    CUDA_CHECK(cudaMalloc(&s.counts, (size_t)nbuckets * 4));
+    CUDA_CHECK(cudaMalloc(&s.offsets, ((size_t)nbuckets + 1) * 4));
+    CUDA_CHECK(cudaMalloc(&s.cursor, (size_t)nbuckets * 4));
+    CUDA_CHECK(cudaMalloc(&s.entries, (nent + 1) * 4));
+    CUDA_CHECK(cudaMalloc(&s.big_list, (size_t)nbuckets * 4));
+    CUDA_CHECK(cudaMalloc(&s.big_count, 4));
+    CUDA_CHECK(cudaMalloc(&s.frag_first, nchunks * pt));
+    CUDA_CHECK(cudaMalloc(&s.frag_last, nchunks * pt));
+    CUDA_CHECK(cudaMalloc(&s.buckets, (size_t)nbuckets * pt));
+    CUDA_CHECK(cudaMalloc(&s.partials, (npart + 1) * pt));
+    CUDA_CHECK(cudaMalloc(&s.result, pt)); s.result_owned = true;
+    CUDA_CHECK(cudaMalloc(&s.scalars_canon, ((size_t)n + 1) * sizeof(fe)));
+}
+
+void msm_scratch_free(MsmScratch& s) {
+    void* ptrs[] = {s.counts, s.offsets, s.cursor, s.entries, s.big_list, s.big_count, s.frag_first, s.frag_last,
+                    s.buckets, s.partials, s.result_owned ? s.result : nullptr, s.scalars_canon};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    s = MsmScratch();
+}
+
+template <class C, class F>
+static void msm_run_t(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st) {
+    using Pt = typename C::Pt;
+    const size_t ptb = sizeof(Pt);
+    if (n > plan.n) n = plan.n;                                  // msm_bigint truncates to the shorter side
+    if (n == 0 || plan.table == nullptr) { CUDA_CHECK(cudaMemsetAsync(s.result, 0, ptb, st)); return; }
+    if (n > s.cap_n || plan.nwin > s.cap_nwin || plan.nbuckets > s.cap_buckets) throw_error(B2G_E_SHAPE, "msm: scratch too small");
+    const uint32_t nb = plan.nbuckets, chunk = s.chunk;
+    CUDA_CHECK(cudaMemsetAsync(s.counts, 0, (size_t)nb * 4, st));
+    msm_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(scalars_dev, n, scalars_mont ? 1 : 0, plan.c, plan.nwin, s.scalars_canon, s.counts);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s.counts, nb, s.offsets, s.cursor, s.big_count);
+    // table rows are indexed w * plan.n + i (the table was built over plan.n bases, n may be shorter)
+    msm_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.scalars_canon, n, plan.n, plan.c, plan.nwin, s.offsets, s.cursor, s.entries);
+    const uint64_t nent = (uint64_t)n * plan.nwin;
+    const uint32_t nthreads = (uint32_t)((nent + chunk - 1) / chunk);
+    msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, 0, st>>>(plan.table, s.entries, s.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
+    msm_fold_kernel<C, F><<<(nb + 127) / 128, 128, 0, st>>>(s.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
+    const size_t sh = (size_t)MSM_TREE_THREADS * ptb;
+    msm_fold_big_kernel<C, F><<<64, MSM_TREE_THREADS, sh, st>>>(s.offsets, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
+    const uint32_t nred = (nb + MSM_REDUCE_CHUNK - 1) / MSM_REDUCE_CHUNK;
+    const uint32_t npart = (nred + MSM_TREE_THREADS - 1) / MSM_TREE_THREADS;
+    msm_reduce_kernel<C, F><<<npart, MSM_TREE_THREADS, sh, st>>>(s.buckets, nb, s.partials);
+    msm_sum_kernel<C, F><<<1, MSM_TREE_THREADS, sh, st>>>(s.partials, npart, s.result);
+    g_launch_count += 9;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void msm_run(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st) {
+    if (plan.g2) msm_run_t<G2, Fq2>(plan, s, scalars_dev, n, scalars_mont, st);
+    else msm_run_t<G1, Fq>(plan, s, scalars_dev, n, scalars_mont, st);
+}
+
+void msm_init_kernels() {
+    const int shg1 = MSM_TREE_THREADS * (int)sizeof(G1::Pt), shg2 = MSM_TREE_THREADS * (int)sizeof(G2::Pt);
+    (void)shg1;
+    // 128 x 256 B = 32 KiB for G2: below the 48 KiB default, no opt-in needed; keep the attribute call for safety
+    CUDA_CHECK(cudaFuncSetAttribute(msm_fold_big_kernel<G2, Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shg2));
+    CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_kernel<G2, Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shg2));
+    CUDA_CHECK(cudaFuncSetAttribute(msm_sum_kernel<G2, Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shg2));
+}
+
+}  // namespace b2g

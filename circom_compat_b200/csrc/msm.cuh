@@ -1,0 +1,61 @@
+// msm.cuh - multi-scalar multiplication sum_i k_i * P_i over BN254 G1 / G2 for a FIXED base set (a proving-key query).
+//
+// Replaces ark-ec 0.5.0 VariableBaseMSM::msm_bigint as called five times by ark-groth16 0.5.0
+// create_proof_with_assignment (call sites /root/reference/src/zkey.rs:903-912, benches/groth16.rs:52-61; restated in
+// SURVEY.md 3.4 / App. C.3).  Same signed base-2^c digit decomposition, but organised for B200:
+//
+//   * the bases never change between proofs, and HBM is 180 GB, so at key-load time every base P_i is expanded into the
+//     affine table T[w][i] = 2^(c*w) * P_i (w = 0..nwin-1).  All windows then share ONE bucket set of 2^(c-1) buckets:
+//     no per-window bucket reduction and no Horner doubling chain on the critical path.
+//   * per proof: (1) digit histogram, (2) exclusive scan, (3) scatter of (table row | sign) into bucket-sorted order
+//     - a counting sort with atomics, no library sort; (4) perfectly load-balanced accumulation: each thread owns a
+//     fixed-length run of the sorted list, mixed-adds its gathered bases in registers (XYZZ), and emits complete
+//     buckets directly and at most two boundary fragments; (5) fragments are folded per bucket (big buckets by a whole
+//     CTA); (6) the weighted bucket sum sum_b (b+1)*B_b by chunked running sums + a shared-memory tree.
+//   Nothing in (1)-(6) synchronises with the host.
+#pragma once
+#include "ec.cuh"
+
+namespace b2g {
+
+constexpr int MSM_MAX_WIN = 32;          // c >= 8
+constexpr int MSM_REDUCE_CHUNK = 16;     // buckets per thread in the weighted reduction
+constexpr int MSM_BIG_FRAGS = 32;        // buckets with more fragments than this are folded by a whole CTA
+
+struct MsmPlan {                         // static per query
+    uint32_t n = 0;                      // number of bases
+    int c = 0, nwin = 0;
+    uint32_t nbuckets = 0;               // 2^(c-1)
+    void* table = nullptr;               // affine [nwin][n]
+    bool g2 = false;
+};
+
+struct MsmScratch {                      // one per in-flight MSM
+    uint32_t cap_n = 0; int cap_nwin = 0; uint32_t cap_buckets = 0; uint32_t chunk = 64;
+    uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *entries = nullptr;
+    uint32_t *big_list = nullptr, *big_count = nullptr;
+    void *frag_first = nullptr, *frag_last = nullptr, *buckets = nullptr, *partials = nullptr, *result = nullptr;
+    fe* scalars_canon = nullptr;         // n canonical scalars (filled by the digit pass)
+    bool g2 = false, result_owned = false;
+};
+
+inline int msm_pick_c(uint32_t n) {
+    int lg = 0; while ((1ull << (lg + 1)) <= n) lg++;
+    int c = lg - 3;
+    if (c < 8) c = 8;
+    if (c > 16) c = 16;
+    return c;
+}
+inline int msm_nwin(int c) { return (255 + c - 1) / c; }
+
+// signed digit of window w given the running carry (ark-ec make_digits)
+__device__ __forceinline__ int32_t msm_digit(const uint32_t* k, int c, int w, uint32_t& carry) {
+    uint32_t off = (uint32_t)w * (uint32_t)c, limb = off >> 5, sh = off & 31u;
+    uint64_t v = limb < 8 ? (uint64_t)k[limb] : 0ull;
+    if (limb + 1 < 8) v |= (uint64_t)k[limb + 1] << 32;
+    uint32_t coef = ((uint32_t)(v >> sh) & ((1u << c) - 1u)) + carry;
+    carry = (coef + (1u << (c - 1))) >> c;
+    return (int32_t)coef - (int32_t)(carry << c);
+}
+
+}  // namespace b2g

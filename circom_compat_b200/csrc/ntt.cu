@@ -1,0 +1,273 @@
+// ntt.cu - the R1CS -> QAP witness map of CircomReduction on the device.
+//
+// Replaces /root/reference/src/circom/qap.rs:23-88 (witness_map_from_matrices) and the ark-poly 0.5.0
+// Radix2EvaluationDomain calls it makes (ifft_in_place / distribute_powers / fft_in_place / pointwise product).
+// The values produced are the same field elements; the schedule is reorganised for the GPU:
+//
+//   a, b (and c = a o b) are written in natural order by the sparse mat-vec (qap.rs:37-58);
+//   iNTT is a decimation-in-frequency transform  (natural in  -> bit-reversed out),
+//   the coset scaling by g^i * n^-1 (qap.rs:63-70) is applied in bit-reversed position,
+//   NTT  is a decimation-in-time transform       (bit-reversed in -> natural out),
+// so no bit-reversal pass exists anywhere.  Stages are grouped into passes of <= 10 index bits; one CTA owns a
+// 1024-element tile in shared memory (8 limb planes of u32, conflict-free for unit-stride butterflies) and runs all
+// stages of its pass there.  The last inverse pass, the scaling and the first forward pass share a tile and are one
+// kernel; the last forward pass also computes h = a*b - c (qap.rs:75-85) before storing.
+#include "fp.cuh"
+#include "ntt.cuh"
+#include "util.cuh"
+
+namespace b2g {
+
+// 2^28-th root of unity 5^((r-1)/2^28) in Montgomery form
+__device__ __forceinline__ fe fr_root_2_28() {
+    fe r; r.l[0] = 0x80d13d9cu; r.l[1] = 0x636e7355u; r.l[2] = 0x2445ffd6u; r.l[3] = 0xa22bf374u;
+    r.l[4] = 0x1eb203d8u; r.l[5] = 0x56452ac0u; r.l[6] = 0x2963f9e7u; r.l[7] = 0x1860ef94u;
+    return r;
+}
+
+// pw[b] = omega_{2n}^(2^b), b = 0..logn ; ninv = n^-1
+__global__ void ntt_setup_kernel(int logn, fe* __restrict__ pw, fe* __restrict__ ninv) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fe g = fr_root_2_28();
+    for (int i = 28; i > logn + 1; i--) g = Fr::sqr(g);
+    for (int b = 0; b <= logn; b++) { pw[b] = g; g = Fr::sqr(g); }
+    fe nn = fe_zero(); nn.l[0] = 1u << logn;          // logn <= 28
+    *ninv = Fr::inv(Fr::from_canonical(nn));
+}
+
+// tw[k] = omega_{2n}^k, ct[k] = n^-1 * omega_{2n}^k, k < n
+__global__ void __launch_bounds__(256) ntt_tables_kernel(int logn, const fe* __restrict__ pw, const fe* __restrict__ ninv,
+                                                         fe* __restrict__ tw, fe* __restrict__ ct) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (1u << logn)) return;
+    fe acc = Fr::one();
+    for (int b = 0; b < logn; b++) if ((k >> b) & 1u) acc = Fr::mul(acc, pw[b]);
+    fe_store(&tw[k], acc);
+    fe_store(&ct[k], Fr::mul(acc, *ninv));
+}
+
+// ------------------------------------------------------------------------------------------------ sparse mat-vec
+// a_i = <A_i, w>, b_i = <B_i, w> (evaluate_constraint, ark-groth16 0.5.0, called at qap.rs:42-43), c_i = a_i*b_i,
+// a[m + j] = w[j] for j < num_inputs (qap.rs:46-50), everything else zero.
+__global__ void __launch_bounds__(256) spmv_kernel(uint32_t n, uint32_t m, uint32_t num_inputs,
+                            const uint32_t* __restrict__ a_rowptr, const uint32_t* __restrict__ a_col, const fe* __restrict__ a_val,
+                            const uint32_t* __restrict__ b_rowptr, const uint32_t* __restrict__ b_col, const fe* __restrict__ b_val,
+                            const fe* __restrict__ w, fe* __restrict__ a, fe* __restrict__ b, fe* __restrict__ c) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe ra = fe_zero(), rb = fe_zero(), rc = fe_zero();
+    if (i < m) {
+        const fe one = Fr::one();
+        for (uint32_t k = a_rowptr[i]; k < a_rowptr[i + 1]; k++) {
+            fe v = fe_load_nc(&a_val[k]); fe x = fe_load_nc(&w[a_col[k]]);
+            ra = Fr::add(ra, fe_equal(v, one) ? x : Fr::mul(v, x));
+        }
+        for (uint32_t k = b_rowptr[i]; k < b_rowptr[i + 1]; k++) {
+            fe v = fe_load_nc(&b_val[k]); fe x = fe_load_nc(&w[b_col[k]]);
+            rb = Fr::add(rb, fe_equal(v, one) ? x : Fr::mul(v, x));
+        }
+        rc = Fr::mul(ra, rb);
+    } else if (i < m + num_inputs) {
+        ra = fe_load_nc(&w[i - m]);
+    }
+    fe_store(&a[i], ra); fe_store(&b[i], rb); fe_store(&c[i], rc);
+}
+
+// ------------------------------------------------------------------------------------------------ tiled passes
+struct NttPassArgs {
+    fe* vec[3];           // in-place vectors
+    fe* out;              // pointwise result (h); may alias vec[0]
+    const fe* tw;         // omega_{2n}^k, k < n
+    const fe* ct;         // n^-1 * omega_{2n}^k
+    int logn, tl;         // tl = log2(tile)
+    int sb, k;            // transform bits [sb, sb + k) of the element index
+    int do_dif, do_scale, do_dit, pointwise;
+};
+
+__device__ __forceinline__ uint32_t tile_global_index(uint32_t loc, uint32_t tile_id, int cols_log, int sb, int k) {
+    uint32_t t = loc >> cols_log, col = loc & ((1u << cols_log) - 1u);
+    uint32_t o = (tile_id << cols_log) | col;
+    uint32_t lo = o & ((1u << sb) - 1u), high = o >> sb;
+    return (high << (sb + k)) | (t << sb) | lo;
+}
+
+__device__ __forceinline__ fe sm_get(const uint32_t* sm, uint32_t tile, uint32_t i) {
+    fe r;
+    #pragma unroll
+    for (int l = 0; l < 8; l++) r.l[l] = sm[l * tile + i];
+    return r;
+}
+__device__ __forceinline__ void sm_put(uint32_t* sm, uint32_t tile, uint32_t i, const fe& v) {
+    #pragma unroll
+    for (int l = 0; l < 8; l++) sm[l * tile + i] = v.l[l];
+}
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const uint32_t tile = 1u << A.tl, half = tile >> 1, tid = threadIdx.x;
+    const int cols_log = A.tl - A.k;
+    const uint32_t n = 1u << A.logn;
+    const uint32_t g0 = tile_global_index(tid, blockIdx.x, cols_log, A.sb, A.k);
+    const uint32_t g1 = tile_global_index(tid + half, blockIdx.x, cols_log, A.sb, A.k);
+    const int nv = A.pointwise ? 3 : 1;
+    fe acc0 = fe_zero(), acc1 = fe_zero();
+    for (int vi = 0; vi < nv; vi++) {
+        fe* vec = A.pointwise ? A.vec[vi] : A.vec[blockIdx.y];
+        if (tid < half || half == 0) {
+            sm_put(sm, tile, tid, fe_load(&vec[g0]));
+            if (half) sm_put(sm, tile, tid + half, fe_load(&vec[g1]));
+        }
+        __syncthreads();
+        if (A.do_dif) {
+            for (int q = A.tl - 1; q >= cols_log; q--) {
+                const int s = A.sb + (q - cols_log);                     // global stage: span 2^s
+                if (tid < half) {
+                    const uint32_t i0 = ((tid >> q) << (q + 1)) | (tid & ((1u << q) - 1u)), i1 = i0 + (1u << q);
+                    const uint32_t gi = tile_global_index(i0, blockIdx.x, cols_log, A.sb, A.k);
+                    const uint32_t j = gi & ((1u << s) - 1u);
+                    const uint32_t e2 = j << (A.logn - s);               // 2 * (j * n / 2^(s+1))
+                    fe u = sm_get(sm, tile, i0), v = sm_get(sm, tile, i1);
+                    sm_put(sm, tile, i0, Fr::add(u, v));
+                    fe d;
+                    if (e2 == 0) d = Fr::sub(u, v);
+                    else d = Fr::mul(Fr::sub(v, u), fe_load_nc(&A.tw[n - e2]));   // omega_n^-e = -omega_2n^(n-2e)
+                    sm_put(sm, tile, i1, d);
+                }
+                __syncthreads();
+            }
+        }
+        if (A.do_scale) {
+            // position p holds coefficient bitrev(p): multiply by n^-1 * g^bitrev(p)   (qap.rs:63-70)
+            if (tid < half || half == 0) {
+                fe x = sm_get(sm, tile, tid);
+                sm_put(sm, tile, tid, Fr::mul(x, fe_load_nc(&A.ct[A.logn ? __brev(g0) >> (32 - A.logn) : 0u])));
+                if (half) {
+                    fe y = sm_get(sm, tile, tid + half);
+                    sm_put(sm, tile, tid + half, Fr::mul(y, fe_load_nc(&A.ct[A.logn ? __brev(g1) >> (32 - A.logn) : 0u])));
+                }
+            }
+            __syncthreads();
+        }
+        if (A.do_dit) {
+            for (int q = cols_log; q < A.tl; q++) {
+                const int s = A.sb + (q - cols_log);
+                if (tid < half) {
+                    const uint32_t i0 = ((tid >> q) << (q + 1)) | (tid & ((1u << q) - 1u)), i1 = i0 + (1u << q);
+                    const uint32_t gi = tile_global_index(i0, blockIdx.x, cols_log, A.sb, A.k);
+                    const uint32_t j = gi & ((1u << s) - 1u);
+                    const uint32_t e2 = j << (A.logn - s);
+                    fe u = sm_get(sm, tile, i0), v = sm_get(sm, tile, i1);
+                    if (e2 != 0) v = Fr::mul(v, fe_load_nc(&A.tw[e2]));
+                    sm_put(sm, tile, i0, Fr::add(u, v));
+                    sm_put(sm, tile, i1, Fr::sub(u, v));
+                }
+                __syncthreads();
+            }
+        }
+        if (tid < half || half == 0) {
+            fe x0 = sm_get(sm, tile, tid), x1 = half ? sm_get(sm, tile, tid + half) : fe_zero();
+            if (!A.pointwise) {
+                fe_store(&vec[g0], x0);
+                if (half) fe_store(&vec[g1], x1);
+            } else if (vi == 0) { acc0 = x0; acc1 = x1; }
+            else if (vi == 1) { acc0 = Fr::mul(acc0, x0); acc1 = Fr::mul(acc1, x1); }
+            else {
+                fe_store(&A.out[g0], Fr::sub(acc0, x0));                  // h = a*b - c   (qap.rs:75-85)
+                if (half) fe_store(&A.out[g1], Fr::sub(acc1, x1));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// out[bitrev(i)] = in[i] * (scale ? *scale : 1)
+__global__ void __launch_bounds__(256) bitrev_copy_kernel(const fe* __restrict__ in, fe* __restrict__ out, int logn, const fe* __restrict__ scale) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << logn)) return;
+    uint32_t j = logn ? (__brev(i) >> (32 - logn)) : 0u;
+    fe v = fe_load(&in[i]);
+    if (scale) v = Fr::mul(v, *scale);
+    fe_store(&out[j], v);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st) {
+    // qap.rs:63-66 also needs the domain of size 2n, so n itself is limited to 2^27
+    if (logn < 0 || logn > 27) throw_error(B2G_E_DOMAIN, "evaluation domain too large (PolynomialDegreeTooLarge)");
+    d.logn = logn;
+    const size_t n = (size_t)1 << logn;
+    CUDA_CHECK(cudaMalloc(&d.tw, n * sizeof(fe)));
+    CUDA_CHECK(cudaMalloc(&d.ct, n * sizeof(fe)));
+    CUDA_CHECK(cudaMalloc(&d.pw, 32 * sizeof(fe)));
+    ntt_setup_kernel<<<1, 1, 0, st>>>(logn, d.pw, d.pw + 30);
+    ntt_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logn, d.pw, d.pw + 30, d.tw, d.ct);
+    CUDA_CHECK(cudaGetLastError());
+    // pass schedule: block pass (bits [0, tl)), then strided passes over the remaining bits, split evenly
+    d.tl = logn < 10 ? logn : 10;
+    d.npass = 0;
+    d.pass_sb[d.npass] = 0; d.pass_k[d.npass] = d.tl; d.npass++;
+    int rem = logn - d.tl;
+    if (rem > 0) {
+        int np = (rem + d.tl - 1) / d.tl, sb = d.tl;
+        for (int p = 0; p < np; p++) {
+            int k = rem / (np - p);                 // even split
+            d.pass_sb[d.npass] = sb; d.pass_k[d.npass] = k; d.npass++;
+            sb += k; rem -= k;
+        }
+    }
+}
+
+void ntt_domain_destroy(NttDomain& d) {
+    if (d.tw) cudaFree(d.tw);
+    if (d.ct) cudaFree(d.ct);
+    if (d.pw) cudaFree(d.pw);
+    d = NttDomain();
+}
+
+static void launch_pass(const NttDomain& d, fe* v0, fe* v1, fe* v2, int nvec, fe* out, int pass, int dif, int scale, int dit, int pointwise,
+                        cudaStream_t st) {
+    NttPassArgs A;
+    A.vec[0] = v0; A.vec[1] = v1; A.vec[2] = v2; A.out = out; A.tw = d.tw; A.ct = d.ct;
+    A.logn = d.logn; A.tl = d.tl; A.sb = d.pass_sb[pass]; A.k = d.pass_k[pass];
+    A.do_dif = dif; A.do_scale = scale; A.do_dit = dit; A.pointwise = pointwise;
+    const uint32_t tile = 1u << d.tl;
+    const uint32_t ntiles = (uint32_t)(((size_t)1 << d.logn) >> d.tl);
+    dim3 grid(ntiles, pointwise ? 1 : nvec);
+    uint32_t threads = tile / 2 ? tile / 2 : 1;
+    ntt_pass_kernel<<<grid, threads, tile * 32, st>>>(A);
+    g_launch_count += 1;
+}
+
+// the three vectors a, b, c (natural order, in place) -> h (natural order) in `out`
+void ntt_witness_transform(const NttDomain& d, fe* a, fe* b, fe* c, fe* out, cudaStream_t st) {
+    for (int p = d.npass - 1; p >= 1; p--) launch_pass(d, a, b, c, 3, nullptr, p, 1, 0, 0, 0, st);
+    const bool single = d.npass == 1;
+    launch_pass(d, a, b, c, 3, out, 0, 1, 1, 1, single ? 1 : 0, st);
+    for (int p = 1; p < d.npass; p++) launch_pass(d, a, b, c, 3, out, p, 0, 0, 1, p == d.npass - 1 ? 1 : 0, st);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+// plain natural-order (i)NTT of one vector (parity entry point b2g_ntt); tmp = scratch of n elements
+void ntt_plain(const NttDomain& d, fe* data, fe* tmp, bool inverse, cudaStream_t st) {
+    const size_t n = (size_t)1 << d.logn;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (inverse) {
+        for (int p = d.npass - 1; p >= 0; p--) launch_pass(d, data, nullptr, nullptr, 1, nullptr, p, 1, 0, 0, 0, st);
+        bitrev_copy_kernel<<<blocks, 256, 0, st>>>(data, tmp, d.logn, d.ct);        // ct[0] = n^-1
+        CUDA_CHECK(cudaMemcpyAsync(data, tmp, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+    } else {
+        bitrev_copy_kernel<<<blocks, 256, 0, st>>>(data, tmp, d.logn, nullptr);
+        CUDA_CHECK(cudaMemcpyAsync(data, tmp, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
+        for (int p = 0; p < d.npass; p++) launch_pass(d, data, nullptr, nullptr, 1, nullptr, p, 0, 0, 1, 0, st);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void spmv_launch(uint32_t n, uint32_t m, uint32_t num_inputs, const uint32_t* a_rowptr, const uint32_t* a_col, const fe* a_val,
+                 const uint32_t* b_rowptr, const uint32_t* b_col, const fe* b_val, const fe* w, fe* a, fe* b, fe* c, cudaStream_t st) {
+    spmv_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, m, num_inputs, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val, w, a, b, c);
+    g_launch_count += 1;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace b2g

@@ -1,0 +1,675 @@
+// prover.cu - contexts, device-resident proving keys / matrices, the proof pipeline and the C ABI (include/b2groth.h).
+//
+// Pipeline of one proof = Groth16::create_proof_with_reduction_and_matrices (call sites /root/reference/src/zkey.rs:903-912,
+// benches/groth16.rs:52-61; body restated in SURVEY.md 3.3/3.4):
+//     stream 0: H2D witness -> sparse mat-vec -> iNTT/coset/NTT -> h (stays in HBM) -> MSM over h_query
+//     streams 1..4: MSMs over l_query / a_query[1..] / b_g1_query[1..] / b_g2_query[1..] against the witness
+//     stream 0: glue (r*delta, s*delta, vk terms, s*A + r*B1 - rs*delta + L + H, three affine conversions) -> D2H 256 B
+#include <atomic>
+#include <cstring>
+#include <vector>
+#include "../../include/b2groth.h"
+#include "ec.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "util.cuh"
+
+namespace b2g {
+
+// from msm.cu
+void msm_build_table(MsmPlan& plan, const void* bases_dev, uint32_t n, bool g2, cudaStream_t st);
+void msm_free_table(MsmPlan& plan);
+void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2);
+void msm_scratch_free(MsmScratch& s);
+void msm_run(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st);
+void msm_init_kernels();
+
+enum { Q_H = 0, Q_L = 1, Q_A = 2, Q_B1 = 3, Q_B2 = 4, NQ = 5 };
+static const size_t PARTIAL_OFF[NQ] = {0, 128, 256, 384, 512};
+
+}  // namespace b2g
+
+using namespace b2g;
+
+struct b2g_ctx {
+    int device = 0, shard_rank = 0, shard_count = 1;
+    cudaStream_t st[NQ] = {};
+    cudaEvent_t ev_w = nullptr, ev_done[NQ] = {}, ev_t[20] = {};
+    MsmScratch scratch[NQ];
+    bool scratch_ok = false;
+    uint8_t* d_partial = nullptr;        // 768 B: [H, L, A, B1] G1 XYZZ + B2 G2 XYZZ
+    uint8_t* d_partials_all = nullptr;   // up to 64 ranks
+    uint8_t* d_proof = nullptr;          // 256 B
+    uint8_t* d_pre = nullptr;            // glue precomputation: r*d1, s*d1, rs*d1 (G1 XYZZ) + s*d2 (G2 XYZZ)
+    fe *d_w = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
+    size_t cap_w = 0, cap_n = 0;
+    float last_ms[16] = {};
+};
+
+struct b2g_pk {
+    b2g_ctx* ctx = nullptr;
+    uint32_t n_vars = 0, n_public = 0, domain = 0;
+    MsmPlan plan[NQ];
+    uint32_t lo[NQ] = {}, cnt[NQ] = {}, scalar_off[NQ] = {};
+    uint8_t* d_consts = nullptr;         // G1: alpha, beta, delta, a_query[0], b_g1_query[0] (5 x 64) ; G2: beta, delta, b_g2_query[0] (3 x 128)
+};
+
+struct b2g_mat {
+    b2g_ctx* ctx = nullptr;
+    uint32_t m = 0, num_inputs = 0, n_vars = 0, n = 0;
+    int logn = 0;
+    NttDomain dom;
+    uint32_t *a_rowptr = nullptr, *a_col = nullptr, *b_rowptr = nullptr, *b_col = nullptr;
+    fe *a_val = nullptr, *b_val = nullptr;
+};
+
+namespace b2g {
+
+static thread_local std::string g_last_error;
+
+template <class Fn>
+static int guarded(Fn&& fn) {
+    try { fn(); return B2G_OK; }
+    catch (const B2gError& e) { g_last_error = e.what(); return e.code; }
+    catch (const std::exception& e) { g_last_error = e.what(); return B2G_E_DEVICE; }
+    catch (...) { g_last_error = "unknown error"; return B2G_E_DEVICE; }
+}
+
+struct Scalar256 { uint32_t l[8]; };
+
+// ------------------------------------------------------------------------------------------------ glue kernels
+// pre[0] = r*delta1, pre[1] = s*delta1, pre[2] = (r*s)*delta1 (G1 XYZZ, 128 B each); then s*delta2 (G2 XYZZ, 256 B)
+__global__ void glue_pre_kernel(const uint8_t* __restrict__ consts, Scalar256 r, Scalar256 s, uint8_t* __restrict__ pre) {
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x & 31) return;
+    if (warp < 3) {
+        G1::Aff d = aff_load<Fq>(consts, 2);
+        Scalar256 k = (warp == 0) ? r : s;
+        if (warp == 2) {
+            fe rm = Fr::from_canonical(*reinterpret_cast<const fe*>(r.l)), sm = Fr::from_canonical(*reinterpret_cast<const fe*>(s.l));
+            fe rs = Fr::to_canonical(Fr::mul(rm, sm));
+            #pragma unroll
+            for (int i = 0; i < 8; i++) k.l[i] = rs.l[i];
+        }
+        G1::Pt p = G1::mul_scalar(G1::from_affine(d), k.l);
+        pt_store<Fq>(pre, warp, p);
+    } else {
+        G2::Aff d = aff_load<Fq2>(consts + 5 * 64, 1);
+        G2::Pt p = G2::mul_scalar(G2::from_affine(d), s.l);
+        pt_store<Fq2>(pre + 3 * 128, 0, p);
+    }
+}
+
+__device__ __forceinline__ void store_canon(uint8_t* out, int slot, const fe& v) { fe_store(out + 32 * slot, Fq::to_canonical(v)); }
+
+// partials = count x 768 B.  Folds them in rank order and assembles the proof (ark-groth16 0.5.0 create_proof_with_assignment).
+__global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count, const uint8_t* __restrict__ consts,
+                                 const uint8_t* __restrict__ pre, Scalar256 r, Scalar256 s, uint8_t* __restrict__ proof) {
+    __shared__ G1::Pt shA, shB1, shsA, shrB1;
+    const int warp = threadIdx.x >> 5;
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (lead && warp < 2) {
+        // A = r*delta1 + a_query[0] + msm_A + alpha1 ;  B1 = s*delta1 + b_g1_query[0] + msm_B1 + beta1
+        G1::Pt acc = pt_load<Fq>(pre, warp);
+        G1::madd(acc, aff_load<Fq>(consts, warp == 0 ? 3 : 4));
+        for (int k = 0; k < count; k++) { G1::Pt q = pt_load<Fq>(partials + (size_t)k * B2G_PARTIAL_BYTES + (warp == 0 ? 256 : 384), 0); G1::add(acc, q); }
+        G1::madd(acc, aff_load<Fq>(consts, warp == 0 ? 0 : 1));
+        if (warp == 0) shA = acc; else shB1 = acc;
+    }
+    if (lead && warp == 2) {
+        // B2 = s*delta2 + b_g2_query[0] + msm_B2 + beta2
+        G2::Pt acc = pt_load<Fq2>(pre + 3 * 128, 0);
+        G2::madd(acc, aff_load<Fq2>(consts + 5 * 64, 2));
+        for (int k = 0; k < count; k++) { G2::Pt q = pt_load<Fq2>(partials + (size_t)k * B2G_PARTIAL_BYTES + 512, 0); G2::add(acc, q); }
+        G2::madd(acc, aff_load<Fq2>(consts + 5 * 64, 0));
+        G2::Aff b = G2::to_affine(acc);
+        store_canon(proof, 2, b.x.c0); store_canon(proof, 3, b.x.c1); store_canon(proof, 4, b.y.c0); store_canon(proof, 5, b.y.c1);
+    }
+    __syncthreads();
+    if (lead && warp == 0) shsA = G1::mul_scalar(shA, s.l);
+    if (lead && warp == 1) shrB1 = G1::mul_scalar(shB1, r.l);            // r == 0 -> infinity: B1 is skipped (prover.rs)
+    if (lead && warp == 3) {
+        G1::Aff a = G1::to_affine(shA);
+        store_canon(proof, 0, a.x); store_canon(proof, 1, a.y);
+    }
+    __syncthreads();
+    if (lead && warp == 0) {
+        // C = s*A + r*B1 - (r*s)*delta1 + msm_L + msm_H
+        G1::Pt acc = shsA;
+        G1::add(acc, shrB1);
+        G1::Pt rsd = G1::neg(pt_load<Fq>(pre, 2));
+        G1::add(acc, rsd);
+        for (int k = 0; k < count; k++) {
+            G1::Pt l = pt_load<Fq>(partials + (size_t)k * B2G_PARTIAL_BYTES + 128, 0); G1::add(acc, l);
+            G1::Pt h = pt_load<Fq>(partials + (size_t)k * B2G_PARTIAL_BYTES, 0); G1::add(acc, h);
+        }
+        G1::Aff c = G1::to_affine(acc);
+        store_canon(proof, 6, c.x); store_canon(proof, 7, c.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small utility kernels
+template <class C, class F>
+__global__ void xyzz_to_affine_kernel(const void* __restrict__ pts, uint32_t n, void* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    aff_store<F>(out, i, C::to_affine(pt_load<F>(pts, i)));
+}
+
+__device__ __forceinline__ fe fe_from_words(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+    fe r; r.l[0] = a0; r.l[1] = a1; r.l[2] = a2; r.l[3] = a3; r.l[4] = a4; r.l[5] = a5; r.l[6] = a6; r.l[7] = a7; return r;
+}
+// standard generators: G1 = (1, 2); G2 = /root/reference/src/zkey.rs:443-463
+__device__ __forceinline__ G1::Aff g1_generator() { G1::Aff g; g.x = Fq::one(); g.y = Fq::add(g.x, g.x); return g; }
+__device__ __forceinline__ G2::Aff g2_generator() {
+    G2::Aff g;
+    g.x.c0 = Fq::from_canonical(fe_from_words(0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu));
+    g.x.c1 = Fq::from_canonical(fe_from_words(0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u));
+    g.y.c0 = Fq::from_canonical(fe_from_words(0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u));
+    g.y.c1 = Fq::from_canonical(fe_from_words(0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u));
+    return g;
+}
+template <class C> struct Gen;
+template <> struct Gen<G1> { static __device__ __forceinline__ G1::Aff get() { return g1_generator(); } };
+template <> struct Gen<G2> { static __device__ __forceinline__ G2::Aff get() { return g2_generator(); } };
+
+// table[w][d-1] = d * 256^w * G (affine), w < 32, d = 1..255
+template <class C, class F>
+__global__ void fixed_table_kernel(void* __restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32u * 255u) return;
+    uint32_t w = i / 255u, d = i % 255u + 1u;
+    uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    k[w >> 2] = d << (8 * (w & 3));
+    typename C::Pt p = C::mul_scalar(C::from_affine(Gen<C>::get()), k);
+    aff_store<F>(table, i, C::to_affine(p));
+}
+template <class C, class F>
+__global__ void __launch_bounds__(128) fixed_base_kernel(const void* __restrict__ table, const fe* __restrict__ scalars, uint32_t n, void* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe k = fe_load_nc(&scalars[i]);
+    typename C::Pt acc = C::infinity();
+    for (int w = 0; w < 32; w++) {
+        uint32_t byte = (k.l[w >> 2] >> (8 * (w & 3))) & 255u;
+        if (byte) C::madd(acc, aff_load<F>(table, (size_t)w * 255u + byte - 1u));
+    }
+    aff_store<F>(out, i, C::to_affine(acc));
+}
+
+__global__ void test_op_kernel(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t n, uint8_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op <= 7) {
+        fe x = fe_load(a + 32 * (size_t)i), y = (op == 6 || op == 7) ? fe_zero() : fe_load(b + 32 * (size_t)i), r;
+        switch (op) {
+            case 0: r = Fq::mul(x, y); break;
+            case 1: r = Fq::add(x, y); break;
+            case 2: r = Fq::sub(x, y); break;
+            case 3: r = Fr::mul(x, y); break;
+            case 4: r = Fr::add(x, y); break;
+            case 5: r = Fr::sub(x, y); break;
+            case 6: r = Fq::inv(x); break;
+            default: r = Fr::inv(x); break;
+        }
+        fe_store(out + 32 * (size_t)i, r);
+    } else if (op == 8 || op == 10) {
+        G1::Aff p = aff_load<Fq>(a, i);
+        G1::Pt acc = G1::from_affine(p);
+        if (op == 8) { G1::Pt q = G1::from_affine(aff_load<Fq>(b, i)); G1::add(acc, q); }   // exercises the full addition
+        else acc = G1::dbl(acc);
+        aff_store<Fq>(out, i, G1::to_affine(acc));
+    } else if (op == 9 || op == 11) {
+        G2::Aff p = aff_load<Fq2>(a, i);
+        G2::Pt acc = G2::from_affine(p);
+        if (op == 9) { G2::Pt q = G2::from_affine(aff_load<Fq2>(b, i)); G2::add(acc, q); }
+        else acc = G2::dbl(acc);
+        aff_store<Fq2>(out, i, G2::to_affine(acc));
+    } else if (op == 12) {      // mixed addition path
+        G1::Pt acc = G1::from_affine(aff_load<Fq>(a, i));
+        G1::madd(acc, aff_load<Fq>(b, i));
+        aff_store<Fq>(out, i, G1::to_affine(acc));
+    } else if (op == 13) {
+        G2::Pt acc = G2::from_affine(aff_load<Fq2>(a, i));
+        G2::madd(acc, aff_load<Fq2>(b, i));
+        aff_store<Fq2>(out, i, G2::to_affine(acc));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+struct DevGuard {
+    int prev = 0;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); CUDA_CHECK(cudaSetDevice(dev)); }
+    ~DevGuard() { cudaSetDevice(prev); }
+};
+
+template <class T>
+static T* dev_upload(const void* host, size_t bytes, cudaStream_t st) {
+    T* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, bytes ? bytes : 1));
+    if (bytes) CUDA_CHECK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
+    return d;
+}
+
+static void ensure_witness_buffers(b2g_ctx* ctx, size_t n_vars, size_t n) {
+    if (n_vars > ctx->cap_w) {
+        if (ctx->d_w) cudaFree(ctx->d_w);
+        CUDA_CHECK(cudaMalloc(&ctx->d_w, (n_vars + 1) * sizeof(fe)));
+        ctx->cap_w = n_vars;
+    }
+    if (n > ctx->cap_n) {
+        for (fe** p : {&ctx->d_a, &ctx->d_b, &ctx->d_c, &ctx->d_h}) { if (*p) cudaFree(*p); CUDA_CHECK(cudaMalloc(p, n * sizeof(fe))); }
+        ctx->cap_n = n;
+    }
+}
+
+static void run_witness_map(b2g_ctx* ctx, b2g_mat* mat, cudaStream_t st) {
+    spmv_launch(mat->n, mat->m, mat->num_inputs, mat->a_rowptr, mat->a_col, mat->a_val, mat->b_rowptr, mat->b_col, mat->b_val,
+                ctx->d_w, ctx->d_a, ctx->d_b, ctx->d_c, st);
+    ntt_witness_transform(mat->dom, ctx->d_a, ctx->d_b, ctx->d_c, ctx->d_h, st);
+}
+
+static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
+    if (!ctx || !pk || !mat) throw_error(B2G_E_SHAPE, "null handle");
+    if (pk->ctx != ctx || mat->ctx != ctx) throw_error(B2G_E_SHAPE, "handle belongs to another context");
+    if (pk->n_vars != mat->n_vars) throw_error(B2G_E_SHAPE, "proving key and matrices disagree on n_vars");
+    if (pk->domain != mat->n) throw_error(B2G_E_SHAPE, "proving key domain_size != next_pow2(num_constraints + num_inputs)");
+    if (pk->n_public + 1 != mat->num_inputs) throw_error(B2G_E_SHAPE, "proving key n_public + 1 != num_inputs");
+}
+
+// device part of a proof up to the five partial MSM results (witness must already be in ctx->d_w)
+static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
+    cudaStream_t s0 = ctx->st[0];
+    CUDA_CHECK(cudaEventRecord(ctx->ev_w, s0));
+    for (int q = 1; q < NQ; q++) {
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_w, 0));
+        if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q], ctx->st[q]));
+        msm_run(pk->plan[q], ctx->scratch[q], ctx->d_w + pk->scalar_off[q] + pk->lo[q], pk->cnt[q], true, ctx->st[q]);
+        if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q + 1], ctx->st[q]));
+        CUDA_CHECK(cudaEventRecord(ctx->ev_done[q], ctx->st[q]));
+    }
+    if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[10], s0));
+    run_witness_map(ctx, mat, s0);
+    if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[11], s0));
+    if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[0], s0));
+    msm_run(pk->plan[Q_H], ctx->scratch[Q_H], ctx->d_h + pk->lo[Q_H], pk->cnt[Q_H], true, s0);
+    if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[1], s0));
+    for (int q = 1; q < NQ; q++) CUDA_CHECK(cudaStreamWaitEvent(s0, ctx->ev_done[q], 0));
+}
+
+static Scalar256 load_scalar(const void* p) { Scalar256 s; memcpy(s.l, p, 32); return s; }
+
+static void launch_glue(b2g_ctx* ctx, b2g_pk* pk, const uint8_t* partials_dev, int count, const void* r, const void* s, cudaStream_t st) {
+    Scalar256 rr = load_scalar(r), ss = load_scalar(s);
+    glue_pre_kernel<<<1, 128, 0, st>>>(pk->d_consts, rr, ss, ctx->d_pre);
+    glue_post_kernel<<<1, 128, 0, st>>>(partials_dev, count, pk->d_consts, ctx->d_pre, rr, ss, ctx->d_proof);
+    g_launch_count += 2;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+static void collect_timings(b2g_ctx* ctx) {
+    auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev_t[a], ctx->ev_t[b]); return ms; };
+    ctx->last_ms[0] = el(12, 13);           // h2d
+    ctx->last_ms[1] = el(10, 11);           // witness map
+    ctx->last_ms[2] = el(0, 1);             // msm H
+    for (int q = 1; q < NQ; q++) ctx->last_ms[2 + q] = el(2 * q, 2 * q + 1);
+    ctx->last_ms[7] = el(14, 15);           // glue + d2h
+    ctx->last_ms[8] = el(12, 15);           // whole call
+}
+
+}  // namespace b2g
+
+// ================================================================================================== C ABI
+extern "C" {
+
+const char* b2g_last_error(void) { return g_last_error.c_str(); }
+int b2g_version(void) { return 1; }
+
+int b2g_device_count(int* count) {
+    return guarded([&] { if (!count) throw_error(B2G_E_SHAPE, "null pointer"); CUDA_CHECK(cudaGetDeviceCount(count)); });
+}
+
+int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
+    return guarded([&] {
+        if (!out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (shard_count < 1 || shard_count > 64 || shard_rank < 0 || shard_rank >= shard_count) throw_error(B2G_E_SHAPE, "bad shard rank/count");
+        int ndev = 0;
+        CUDA_CHECK(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) throw_error(B2G_E_DEVICE, "no such CUDA device (this library has no CPU fallback)");
+        DevGuard g(device);
+        b2g_ctx* ctx = new b2g_ctx();
+        ctx->device = device; ctx->shard_rank = shard_rank; ctx->shard_count = shard_count;
+        for (int i = 0; i < NQ; i++) { CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st[i], cudaStreamNonBlocking)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_w, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_t) CUDA_CHECK(cudaEventCreate(&e));
+        CUDA_CHECK(cudaMalloc(&ctx->d_partial, B2G_PARTIAL_BYTES));
+        CUDA_CHECK(cudaMalloc(&ctx->d_partials_all, 64 * B2G_PARTIAL_BYTES));
+        CUDA_CHECK(cudaMalloc(&ctx->d_proof, 256));
+        CUDA_CHECK(cudaMalloc(&ctx->d_pre, 3 * 128 + 256));
+        msm_init_kernels();
+        *out = ctx;
+    });
+}
+
+int b2g_ctx_destroy(b2g_ctx* ctx) {
+    return guarded([&] {
+        if (!ctx) return;
+        DevGuard g(ctx->device);
+        cudaDeviceSynchronize();
+        for (int i = 0; i < NQ; i++) { if (ctx->scratch_ok) msm_scratch_free(ctx->scratch[i]); cudaStreamDestroy(ctx->st[i]); cudaEventDestroy(ctx->ev_done[i]); }
+        cudaEventDestroy(ctx->ev_w);
+        for (auto& e : ctx->ev_t) cudaEventDestroy(e);
+        for (void* p : {(void*)ctx->d_partial, (void*)ctx->d_partials_all, (void*)ctx->d_proof, (void*)ctx->d_pre, (void*)ctx->d_w,
+                        (void*)ctx->d_a, (void*)ctx->d_b, (void*)ctx->d_c, (void*)ctx->d_h}) if (p) cudaFree(p);
+        delete ctx;
+    });
+}
+
+int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
+    return guarded([&] {
+        if (!ctx || !d || !out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (d->n_vars < d->n_public + 1 || d->domain_size == 0) throw_error(B2G_E_SHAPE, "bad proving-key header");
+        for (const void* p : {d->alpha_g1, d->beta_g1, d->delta_g1, d->beta_g2, d->delta_g2, d->a_query, d->b_g1_query, d->b_g2_query, d->h_query})
+            if (!p) throw_error(B2G_E_SHAPE, "null proving-key section");
+        DevGuard g(ctx->device);
+        cudaStream_t st = ctx->st[0];
+        b2g_pk* pk = new b2g_pk();
+        pk->ctx = ctx; pk->n_vars = d->n_vars; pk->n_public = d->n_public; pk->domain = d->domain_size;
+        const uint32_t li = d->n_public + 1;
+        // query sizes as paired with scalars by create_proof_with_assignment
+        const uint32_t total[NQ] = {d->domain_size, d->n_vars - li, d->n_vars - 1, d->n_vars - 1, d->n_vars - 1};
+        const uint32_t base_skip[NQ] = {0, 0, 1, 1, 1};             // query[0] is added separately for A/B1/B2
+        const uint32_t soff[NQ] = {0, li, 1, 1, 1};                 // first scalar: h[0] / w[l] / w[1]
+        const void* src[NQ] = {d->h_query, d->l_query, d->a_query, d->b_g1_query, d->b_g2_query};
+        for (int q = 0; q < NQ; q++) {
+            const bool g2 = q == Q_B2;
+            const size_t aff = g2 ? 128 : 64;
+            const uint64_t R = ctx->shard_count, r = ctx->shard_rank;
+            pk->lo[q] = (uint32_t)((uint64_t)total[q] * r / R);
+            pk->cnt[q] = (uint32_t)((uint64_t)total[q] * (r + 1) / R) - pk->lo[q];
+            pk->scalar_off[q] = soff[q];
+            if (total[q] && !src[q]) throw_error(B2G_E_SHAPE, "null proving-key section");
+            void* tmp = nullptr;
+            if (pk->cnt[q]) tmp = dev_upload<uint8_t>((const uint8_t*)src[q] + (size_t)(base_skip[q] + pk->lo[q]) * aff, (size_t)pk->cnt[q] * aff, st);
+            msm_build_table(pk->plan[q], tmp, pk->cnt[q], g2, st);
+            g_launch_count += 1;
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (tmp) cudaFree(tmp);
+        }
+        std::vector<uint8_t> consts(5 * 64 + 3 * 128);
+        memcpy(&consts[0], d->alpha_g1, 64); memcpy(&consts[64], d->beta_g1, 64); memcpy(&consts[128], d->delta_g1, 64);
+        memcpy(&consts[192], d->a_query, 64); memcpy(&consts[256], d->b_g1_query, 64);
+        memcpy(&consts[320], d->beta_g2, 128); memcpy(&consts[448], d->delta_g2, 128); memcpy(&consts[576], d->b_g2_query, 128);
+        pk->d_consts = dev_upload<uint8_t>(consts.data(), consts.size(), st);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        // per-stream MSM scratch sized for this key (re-created if a later key is larger)
+        if (ctx->scratch_ok) { for (int q = 0; q < NQ; q++) msm_scratch_free(ctx->scratch[q]); ctx->scratch_ok = false; }
+        for (int q = 0; q < NQ; q++) {
+            const MsmPlan& p = pk->plan[q];
+            msm_scratch_alloc(ctx->scratch[q], p.n ? p.n : 1, p.nwin, p.nbuckets, q == Q_B2);
+            cudaFree(ctx->scratch[q].result);
+            ctx->scratch[q].result = ctx->d_partial + PARTIAL_OFF[q];
+            ctx->scratch[q].result_owned = false;
+        }
+        ctx->scratch_ok = true;
+        *out = pk;
+    });
+}
+
+int b2g_pk_free(b2g_pk* pk) {
+    return guarded([&] {
+        if (!pk) return;
+        DevGuard g(pk->ctx->device);
+        cudaDeviceSynchronize();
+        for (int q = 0; q < NQ; q++) msm_free_table(pk->plan[q]);
+        if (pk->d_consts) cudaFree(pk->d_consts);
+        delete pk;
+    });
+}
+
+int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
+    return guarded([&] {
+        if (!ctx || !d || !out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (!d->a_rowptr || !d->b_rowptr) throw_error(B2G_E_SHAPE, "null row pointer array");
+        if (d->num_inputs == 0 || d->num_inputs > d->n_vars) throw_error(B2G_E_SHAPE, "num_inputs out of range");
+        const uint64_t need = (uint64_t)d->num_constraints + d->num_inputs;
+        int logn = 0;
+        while ((1ull << logn) < need) logn++;
+        if (logn > 27) throw_error(B2G_E_DOMAIN, "PolynomialDegreeTooLarge: domain (and its double) must fit 2^28");
+        const uint32_t m = d->num_constraints;
+        const uint32_t annz = d->a_rowptr[m], bnnz = d->b_rowptr[m];
+        if ((annz && (!d->a_col || !d->a_val)) || (bnnz && (!d->b_col || !d->b_val))) throw_error(B2G_E_SHAPE, "null matrix arrays");
+        for (uint32_t k = 0; k < annz; k++) if (d->a_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix A column index out of range");
+        for (uint32_t k = 0; k < bnnz; k++) if (d->b_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix B column index out of range");
+        DevGuard g(ctx->device);
+        cudaStream_t st = ctx->st[0];
+        b2g_mat* mat = new b2g_mat();
+        mat->ctx = ctx; mat->m = m; mat->num_inputs = d->num_inputs; mat->n_vars = d->n_vars; mat->logn = logn; mat->n = 1u << logn;
+        mat->a_rowptr = dev_upload<uint32_t>(d->a_rowptr, ((size_t)m + 1) * 4, st);
+        mat->b_rowptr = dev_upload<uint32_t>(d->b_rowptr, ((size_t)m + 1) * 4, st);
+        mat->a_col = dev_upload<uint32_t>(d->a_col, (size_t)annz * 4, st);
+        mat->b_col = dev_upload<uint32_t>(d->b_col, (size_t)bnnz * 4, st);
+        mat->a_val = dev_upload<fe>(d->a_val, (size_t)annz * 32, st);
+        mat->b_val = dev_upload<fe>(d->b_val, (size_t)bnnz * 32, st);
+        ntt_domain_create(mat->dom, logn, st);
+        g_launch_count += 2;
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        *out = mat;
+    });
+}
+
+int b2g_matrices_free(b2g_mat* mat) {
+    return guarded([&] {
+        if (!mat) return;
+        DevGuard g(mat->ctx->device);
+        cudaDeviceSynchronize();
+        ntt_domain_destroy(mat->dom);
+        for (void* p : {(void*)mat->a_rowptr, (void*)mat->a_col, (void*)mat->b_rowptr, (void*)mat->b_col, (void*)mat->a_val, (void*)mat->b_val}) if (p) cudaFree(p);
+        delete mat;
+    });
+}
+
+int b2g_witness_map(b2g_ctx* ctx, b2g_mat* mat, const void* w_mont, void* h_out, uint32_t* domain_size_out) {
+    return guarded([&] {
+        if (!ctx || !mat || !w_mont) throw_error(B2G_E_SHAPE, "null pointer");
+        if (mat->ctx != ctx) throw_error(B2G_E_SHAPE, "handle belongs to another context");
+        DevGuard g(ctx->device);
+        cudaStream_t st = ctx->st[0];
+        ensure_witness_buffers(ctx, mat->n_vars, mat->n);
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_w, w_mont, (size_t)mat->n_vars * 32, cudaMemcpyHostToDevice, st));
+        run_witness_map(ctx, mat, st);
+        if (h_out) CUDA_CHECK(cudaMemcpyAsync(h_out, ctx->d_h, (size_t)mat->n * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (domain_size_out) *domain_size_out = mat->n;
+    });
+}
+
+static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont) {
+    check_shapes(ctx, pk, mat);
+    if (!w_mont) throw_error(B2G_E_SHAPE, "null witness");
+    ensure_witness_buffers(ctx, mat->n_vars, mat->n);
+    cudaStream_t s0 = ctx->st[0];
+    CUDA_CHECK(cudaEventRecord(ctx->ev_t[12], s0));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_w, w_mont, (size_t)mat->n_vars * 32, cudaMemcpyHostToDevice, s0));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_t[13], s0));
+    launch_msms(ctx, pk, mat, true);
+}
+
+int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, uint8_t proof_out[256]) {
+    return guarded([&] {
+        if (!ctx || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (ctx->shard_count != 1) throw_error(B2G_E_SHAPE, "b2g_prove needs an unsharded context; use b2g_prove_partial/finish");
+        DevGuard g(ctx->device);
+        prove_common(ctx, pk, mat, w_mont);
+        cudaStream_t s0 = ctx->st[0];
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
+        launch_glue(ctx, pk, ctx->d_partial, 1, r_canon, s_canon, s0);
+        CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+        collect_timings(ctx);
+    });
+}
+
+int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont, void* partial_out) {
+    return guarded([&] {
+        if (!ctx || !partial_out) throw_error(B2G_E_SHAPE, "null pointer");
+        DevGuard g(ctx->device);
+        prove_common(ctx, pk, mat, w_mont);
+        cudaStream_t s0 = ctx->st[0];
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
+        CUDA_CHECK(cudaMemcpyAsync(partial_out, ctx->d_partial, B2G_PARTIAL_BYTES, cudaMemcpyDeviceToHost, s0));
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+        collect_timings(ctx);
+    });
+}
+
+int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int count, const void* r_canon, const void* s_canon, uint8_t proof_out[256]) {
+    return guarded([&] {
+        if (!ctx || !pk || !partials_all || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (count < 1 || count > 64) throw_error(B2G_E_SHAPE, "partial count out of range");
+        DevGuard g(ctx->device);
+        cudaStream_t s0 = ctx->st[0];
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_partials_all, partials_all, (size_t)count * B2G_PARTIAL_BYTES, cudaMemcpyHostToDevice, s0));
+        launch_glue(ctx, pk, ctx->d_partials_all, count, r_canon, s_canon, s0);
+        CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+    });
+}
+
+int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* avg_ms) {
+    return guarded([&] {
+        if (!avg_ms || iters < 1) throw_error(B2G_E_SHAPE, "bad arguments");
+        check_shapes(ctx, pk, mat);
+        if (ctx->cap_w < mat->n_vars) throw_error(B2G_E_SHAPE, "no witness resident: call b2g_prove first");
+        DevGuard g(ctx->device);
+        cudaStream_t s0 = ctx->st[0];
+        Scalar256 one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[16], s0));
+        for (int it = 0; it < iters; it++) {
+            launch_msms(ctx, pk, mat, false);
+            launch_glue(ctx, pk, ctx->d_partial, 1, one.l, one.l, s0);
+        }
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[17], s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+        float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t[16], ctx->ev_t[17]));
+        *avg_ms = ms / iters;
+    });
+}
+
+int b2g_last_timings(b2g_ctx* ctx, float out_ms[16]) {
+    return guarded([&] { if (!ctx || !out_ms) throw_error(B2G_E_SHAPE, "null pointer"); memcpy(out_ms, ctx->last_ms, sizeof(ctx->last_ms)); });
+}
+
+int b2g_launch_count(b2g_ctx* ctx, uint64_t* count) {
+    return guarded([&] { if (!ctx || !count) throw_error(B2G_E_SHAPE, "null pointer"); *count = g_launch_count.load(); });
+}
+
+// ---------------------------------------------------------------------------------------- kernel-level entry points
+}  // extern "C"
+template <bool IS_G2>
+static void msm_entry(b2g_ctx* ctx, const void* bases, const void* scalars, size_t n, int scalars_mont, void* out) {
+    if (!ctx || !out || (n && (!bases || !scalars))) throw_error(B2G_E_SHAPE, "null pointer");
+    if (n >= (1ull << 27)) throw_error(B2G_E_SHAPE, "msm too large");
+    DevGuard g(ctx->device);
+    cudaStream_t st = ctx->st[0];
+    const size_t aff = IS_G2 ? 128 : 64, ptb = 2 * aff;
+    if (n == 0) { memset(out, 0, aff); return; }
+    uint8_t* d_bases = dev_upload<uint8_t>(bases, n * aff, st);
+    fe* d_sc = dev_upload<fe>(scalars, n * 32, st);
+    MsmPlan plan; MsmScratch sc;
+    msm_build_table(plan, d_bases, (uint32_t)n, IS_G2, st);
+    msm_scratch_alloc(sc, (uint32_t)n, plan.nwin, plan.nbuckets, IS_G2);
+    msm_run(plan, sc, d_sc, (uint32_t)n, scalars_mont != 0, st);
+    uint8_t* d_out = nullptr; CUDA_CHECK(cudaMalloc(&d_out, aff));
+    if (IS_G2) xyzz_to_affine_kernel<G2, Fq2><<<1, 1, 0, st>>>(sc.result, 1, d_out);
+    else xyzz_to_affine_kernel<G1, Fq><<<1, 1, 0, st>>>(sc.result, 1, d_out);
+    g_launch_count += 2;
+    CUDA_CHECK(cudaMemcpyAsync(out, d_out, aff, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    (void)ptb;
+    cudaFree(d_out); cudaFree(d_bases); cudaFree(d_sc); msm_free_table(plan); msm_scratch_free(sc);
+    CUDA_CHECK(e);
+}
+
+extern "C" {
+int b2g_msm_g1(b2g_ctx* ctx, const void* bases, const void* scalars, size_t n, int scalars_mont, void* out) {
+    return guarded([&] { msm_entry<false>(ctx, bases, scalars, n, scalars_mont, out); });
+}
+int b2g_msm_g2(b2g_ctx* ctx, const void* bases, const void* scalars, size_t n, int scalars_mont, void* out) {
+    return guarded([&] { msm_entry<true>(ctx, bases, scalars, n, scalars_mont, out); });
+}
+
+int b2g_ntt(b2g_ctx* ctx, void* data, int log_n, int inverse) {
+    return guarded([&] {
+        if (!ctx || !data) throw_error(B2G_E_SHAPE, "null pointer");
+        DevGuard g(ctx->device);
+        cudaStream_t st = ctx->st[0];
+        NttDomain dom;
+        ntt_domain_create(dom, log_n, st);
+        const size_t bytes = ((size_t)1 << log_n) * 32;
+        fe* d = dev_upload<fe>(data, bytes, st);
+        fe* tmp = nullptr; CUDA_CHECK(cudaMalloc(&tmp, bytes));
+        ntt_plain(dom, d, tmp, inverse != 0, st);
+        CUDA_CHECK(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, st));
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(d); cudaFree(tmp); ntt_domain_destroy(dom);
+        CUDA_CHECK(e);
+    });
+}
+
+}  // extern "C"
+template <class C, class F>
+static void fixed_base_entry(b2g_ctx* ctx, const void* scalars, size_t n, void* out) {
+    if (!ctx || (n && (!scalars || !out))) throw_error(B2G_E_SHAPE, "null pointer");
+    if (n == 0) return;
+    DevGuard g(ctx->device);
+    cudaStream_t st = ctx->st[0];
+    const size_t aff = 2 * Bytes<F>::ELEM;
+    void* table = nullptr; CUDA_CHECK(cudaMalloc(&table, 32 * 255 * aff));
+    fixed_table_kernel<C, F><<<(32 * 255 + 63) / 64, 64, 0, st>>>(table);
+    const size_t CH = 1u << 22;                                        // bound temporary device memory
+    fe* d_sc = nullptr; uint8_t* d_out = nullptr;
+    CUDA_CHECK(cudaMalloc(&d_sc, (n < CH ? n : CH) * 32)); CUDA_CHECK(cudaMalloc(&d_out, (n < CH ? n : CH) * aff));
+    cudaError_t e = cudaSuccess;
+    for (size_t off = 0; off < n && e == cudaSuccess; off += CH) {
+        const size_t cnt = n - off < CH ? n - off : CH;
+        cudaMemcpyAsync(d_sc, (const uint8_t*)scalars + off * 32, cnt * 32, cudaMemcpyHostToDevice, st);
+        fixed_base_kernel<C, F><<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(table, d_sc, (uint32_t)cnt, d_out);
+        g_launch_count += 1;
+        cudaMemcpyAsync((uint8_t*)out + off * aff, d_out, cnt * aff, cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(table); cudaFree(d_sc); cudaFree(d_out);
+    CUDA_CHECK(e);
+}
+
+extern "C" {
+int b2g_fixed_base_g1(b2g_ctx* ctx, const void* scalars_canon, size_t n, void* out) {
+    return guarded([&] { fixed_base_entry<G1, Fq>(ctx, scalars_canon, n, out); });
+}
+int b2g_fixed_base_g2(b2g_ctx* ctx, const void* scalars_canon, size_t n, void* out) {
+    return guarded([&] { fixed_base_entry<G2, Fq2>(ctx, scalars_canon, n, out); });
+}
+
+int b2g_test_op(b2g_ctx* ctx, int op, const void* a, const void* b, size_t n, void* out) {
+    return guarded([&] {
+        if (!ctx || !a || !out || op < 0 || op > 13) throw_error(B2G_E_SHAPE, "bad arguments");
+        if (n == 0) return;
+        DevGuard g(ctx->device);
+        cudaStream_t st = ctx->st[0];
+        const size_t esz = op <= 7 ? 32 : ((op == 9 || op == 11 || op == 13) ? 128 : 64);
+        uint8_t* da = dev_upload<uint8_t>(a, n * esz, st);
+        uint8_t* db = dev_upload<uint8_t>(b ? b : a, n * esz, st);
+        uint8_t* dout = nullptr; CUDA_CHECK(cudaMalloc(&dout, n * esz));
+        test_op_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(op, da, db, (uint32_t)n, dout);
+        g_launch_count += 1;
+        CUDA_CHECK(cudaMemcpyAsync(out, dout, n * esz, cudaMemcpyDeviceToHost, st));
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(da); cudaFree(db); cudaFree(dout);
+        CUDA_CHECK(e);
+    });
+}
+
+}  // extern "C"

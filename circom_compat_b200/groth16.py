@@ -1,0 +1,245 @@
+"""Host-side mirror of the proving entry points ark-circom users call, running on libb2groth.so.
+
+    Groth16.create_proof_with_reduction_and_matrices(pk, r, s, matrices, num_inputs, num_constraints, full_assignment)
+        <- Groth16::<Bn254, CircomReduction>::create_proof_with_reduction_and_matrices
+           (/root/reference/src/zkey.rs:903-912, benches/groth16.rs:52-61)
+    CircomReduction.witness_map_from_matrices(matrices, num_inputs, num_constraints, full_assignment)
+        <- /root/reference/src/circom/qap.rs:23-88
+    Groth16.prove(pk, matrices, full_assignment, rng)
+        <- Groth16::<Bn254, CircomReduction>::prove (src/zkey.rs:866): draws r then s, then the call above.
+Arguments keep the reference's meaning; field elements are (n, 4) uint64 Montgomery limb arrays (fr_to_mont).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+from .zkey import ConstraintMatrices, ProvingKey, R_MOD
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+
+
+def _c(a, dtype=np.uint64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One b2g_ctx = one GPU (optionally one shard of a base-range-sharded prover)."""
+
+    def __init__(self, device: int = 0, shard_rank: int = 0, shard_count: int = 1):
+        self._h = C.c_void_p()
+        N.check(N.lib().b2g_ctx_create(device, shard_rank, shard_count, C.byref(self._h)))
+        self.device, self.shard_rank, self.shard_count = device, shard_rank, shard_count
+        self._pks, self._mats = {}, {}
+
+    def close(self):
+        if self._h:
+            for h in self._pks.values():
+                N.lib().b2g_pk_free(h[0])
+            for h in self._mats.values():
+                N.lib().b2g_matrices_free(h[0])
+            self._pks.clear(); self._mats.clear()
+            N.lib().b2g_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # device-resident handles are cached per (ctx, host object)
+    def pk_handle(self, pk: ProvingKey):
+        key = id(pk)
+        if key not in self._pks:
+            d = N.PkDesc()
+            d.n_vars, d.n_public, d.domain_size = pk.n_vars, pk.n_public, pk.domain_size
+            keep = {}
+            for name in ('alpha_g1', 'beta_g1', 'delta_g1', 'beta_g2', 'delta_g2', 'a_query', 'b_g1_query', 'b_g2_query', 'l_query', 'h_query'):
+                keep[name] = _c(getattr(pk, name))
+                setattr(d, name, keep[name].ctypes.data if keep[name].size else None)
+            h = C.c_void_p()
+            N.check(N.lib().b2g_pk_load(self._h, C.byref(d), C.byref(h)))
+            self._pks[key] = (h, pk)
+        return self._pks[key][0]
+
+    def mat_handle(self, m: ConstraintMatrices, n_vars: int):
+        key = id(m)
+        if key not in self._mats:
+            d = N.MatDesc()
+            d.num_constraints, d.num_inputs, d.n_vars = m.num_constraints, m.num_instance_variables, n_vars
+            keep = [_c(m.a[0], np.uint32), _c(m.a[1], np.uint32), _c(m.a[2]), _c(m.b[0], np.uint32), _c(m.b[1], np.uint32), _c(m.b[2])]
+            for name, arr in zip(('a_rowptr', 'a_col', 'a_val', 'b_rowptr', 'b_col', 'b_val'), keep):
+                setattr(d, name, arr.ctypes.data if arr.size else None)
+            h = C.c_void_p()
+            N.check(N.lib().b2g_matrices_load(self._h, C.byref(d), C.byref(h)))
+            self._mats[key] = (h, m)
+        return self._mats[key][0]
+
+    def last_timings(self) -> dict:
+        buf = (C.c_float * 16)()
+        N.check(N.lib().b2g_last_timings(self._h, buf))
+        names = ('h2d', 'witness_map', 'msm_h', 'msm_l', 'msm_a', 'msm_b1', 'msm_b2', 'glue_d2h', 'total')
+        return dict(zip(names, list(buf)[:9]))
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        N.check(N.lib().b2g_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # kernel-level entry points -------------------------------------------------------------
+    def msm_g1(self, bases, scalars, scalars_mont=False) -> np.ndarray:
+        bases, scalars = _c(bases), _c(scalars)
+        n = min(bases.size // 8, scalars.size // 4)
+        out = np.zeros(8, dtype=np.uint64)
+        N.check(N.lib().b2g_msm_g1(self._h, _ptr(bases), _ptr(scalars), n, int(scalars_mont), _ptr(out)))
+        return out
+
+    def msm_g2(self, bases, scalars, scalars_mont=False) -> np.ndarray:
+        bases, scalars = _c(bases), _c(scalars)
+        n = min(bases.size // 16, scalars.size // 4)
+        out = np.zeros(16, dtype=np.uint64)
+        N.check(N.lib().b2g_msm_g2(self._h, _ptr(bases), _ptr(scalars), n, int(scalars_mont), _ptr(out)))
+        return out
+
+    def ntt(self, data_mont, inverse=False) -> np.ndarray:
+        d = _c(data_mont).copy()
+        n = d.size // 4
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise ValueError("ntt length must be a power of two")
+        N.check(N.lib().b2g_ntt(self._h, _ptr(d), log_n, int(inverse)))
+        return d
+
+    def fixed_base_g1(self, scalars_canon) -> np.ndarray:
+        sc = _c(scalars_canon); n = sc.size // 4
+        out = np.zeros((n, 8), dtype=np.uint64)
+        N.check(N.lib().b2g_fixed_base_g1(self._h, _ptr(sc), n, _ptr(out)))
+        return out
+
+    def fixed_base_g2(self, scalars_canon) -> np.ndarray:
+        sc = _c(scalars_canon); n = sc.size // 4
+        out = np.zeros((n, 16), dtype=np.uint64)
+        N.check(N.lib().b2g_fixed_base_g2(self._h, _ptr(sc), n, _ptr(out)))
+        return out
+
+    def test_op(self, op: int, a, b=None) -> np.ndarray:
+        a = _c(a); b = _c(b) if b is not None else None
+        words = 4 if op <= 7 else (16 if op in (9, 11, 13) else 8)
+        n = a.size // words
+        out = np.zeros_like(a)
+        N.check(N.lib().b2g_test_op(self._h, op, _ptr(a), _ptr(b) if b is not None else None, n, _ptr(out)))
+        return out
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+@dataclass
+class Proof:
+    """Proof<Bn254>{a: G1Affine, b: G2Affine, c: G1Affine}; `data` is the 256-byte uncompressed canonical view."""
+    data: bytes
+
+    def _int(self, i):
+        return int.from_bytes(self.data[32 * i:32 * i + 32], 'little')
+
+    @property
+    def a(self):
+        return (self._int(0), self._int(1))
+
+    @property
+    def b(self):
+        return ((self._int(2), self._int(3)), (self._int(4), self._int(5)))
+
+    @property
+    def c(self):
+        return (self._int(6), self._int(7))
+
+
+def _scalar_bytes(v) -> np.ndarray:
+    if isinstance(v, (int, np.integer)):
+        return np.frombuffer((int(v) % R_MOD).to_bytes(32, 'little'), dtype='<u8').copy()
+    a = _c(v).reshape(-1)
+    if a.size != 4:
+        raise ValueError("scalar must be an int or 4 uint64 limbs (canonical)")
+    return a
+
+
+class CircomReduction:
+    """R1CSToQAP implementation selected by Groth16<Bn254, CircomReduction> (src/circom/qap.rs:12-14)."""
+
+    @staticmethod
+    def witness_map_from_matrices(matrices: ConstraintMatrices, num_inputs: int, num_constraints: int, full_assignment, ctx: Context = None) -> np.ndarray:
+        ctx = ctx or default_context()
+        if num_inputs != matrices.num_instance_variables or num_constraints != matrices.num_constraints:
+            raise ValueError("num_inputs / num_constraints disagree with the matrices")
+        w = _c(full_assignment)
+        n_vars = w.size // 4
+        mh = ctx.mat_handle(matrices, n_vars)
+        n = 1
+        while n < num_constraints + num_inputs:
+            n <<= 1
+        h = np.zeros((n, 4), dtype=np.uint64)
+        dom = C.c_uint32()
+        N.check(N.lib().b2g_witness_map(ctx._h, mh, _ptr(w), _ptr(h), C.byref(dom)))
+        assert dom.value == n
+        return h
+
+
+class Groth16:
+    """Groth16::<Bn254, CircomReduction>."""
+
+    @staticmethod
+    def create_proof_with_reduction_and_matrices(pk: ProvingKey, r, s, matrices: ConstraintMatrices, num_inputs: int,
+                                                 num_constraints: int, full_assignment, ctx: Context = None) -> Proof:
+        ctx = ctx or default_context()
+        if num_inputs != matrices.num_instance_variables or num_constraints != matrices.num_constraints:
+            raise ValueError("num_inputs / num_constraints disagree with the matrices")
+        w = _c(full_assignment)
+        if w.size // 4 != pk.n_vars:
+            raise ValueError("full_assignment length != n_vars")
+        ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars)
+        rr, ss = _scalar_bytes(r), _scalar_bytes(s)
+        out = np.zeros(256, dtype=np.uint8)
+        N.check(N.lib().b2g_prove(ctx._h, ph, mh, _ptr(rr), _ptr(ss), _ptr(w), _ptr(out)))
+        return Proof(out.tobytes())
+
+    @staticmethod
+    def prove(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, rng, ctx: Context = None) -> Proof:
+        """Draws r then s like create_random_proof_with_reduction (ark-groth16 0.5.0); rng is any object with
+        randrange (e.g. random.Random / secrets.SystemRandom).  NB: arkworks' Fr::rand interprets the sampled limbs
+        as a Montgomery residue; the distribution is uniform either way."""
+        r = rng.randrange(R_MOD)
+        s = rng.randrange(R_MOD)
+        return Groth16.create_proof_with_reduction_and_matrices(pk, r, s, matrices, matrices.num_instance_variables,
+                                                                matrices.num_constraints, full_assignment, ctx)
+
+    # base-range sharded variant: every rank calls prove_partial, the 768-byte partials are all-gathered by the caller
+    # (torch.distributed / NCCL), then every rank calls prove_finish and obtains the same proof.
+    @staticmethod
+    def prove_partial(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, ctx: Context) -> np.ndarray:
+        w = _c(full_assignment)
+        ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars)
+        out = np.zeros(N.PARTIAL_BYTES, dtype=np.uint8)
+        N.check(N.lib().b2g_prove_partial(ctx._h, ph, mh, _ptr(w), _ptr(out)))
+        return out
+
+    @staticmethod
+    def prove_finish(pk: ProvingKey, partials: np.ndarray, r, s, ctx: Context) -> Proof:
+        parts = np.ascontiguousarray(partials, dtype=np.uint8).reshape(-1, N.PARTIAL_BYTES)
+        rr, ss = _scalar_bytes(r), _scalar_bytes(s)
+        out = np.zeros(256, dtype=np.uint8)
+        N.check(N.lib().b2g_prove_finish(ctx._h, ctx.pk_handle(pk), _ptr(parts), parts.shape[0], _ptr(rr), _ptr(ss), _ptr(out)))
+        return Proof(out.tobytes())

@@ -1,0 +1,144 @@
+/* b2groth.h - C ABI of libb2groth.so, the B200-native (sm_100a CUDA) Groth16/BN254 prover hot path that stands in
+ * for what ark-circom 0.5 obtains from ark-groth16 / ark-ec / ark-poly on the CPU.
+ *
+ * The reference (arkworks-rs/circom-compat) has no FFI; its extension points are Rust traits and generic functions.
+ * Each entry point below names the reference interface it replaces (paths relative to /root/reference):
+ *
+ *   b2g_pk_load            <- the ProvingKey<Bn254> half of read_zkey()                    src/zkey.rs:53-60, 103-133
+ *   b2g_matrices_load      <- the ConstraintMatrices<Fr> half of read_zkey()               src/zkey.rs:151-196
+ *   b2g_witness_map        <- CircomReduction::witness_map_from_matrices                   src/circom/qap.rs:23-88
+ *   b2g_prove              <- Groth16::<Bn254, CircomReduction>::create_proof_with_reduction_and_matrices
+ *                             (call sites src/zkey.rs:903-912, benches/groth16.rs:52-61, 72-80; body = ark-groth16
+ *                             0.5.0 create_proof_with_assignment, restated in SURVEY.md 3.4)
+ *   b2g_msm_g1 / b2g_msm_g2<- VariableBaseMSM::msm_bigint (ark-ec 0.5.0) as used by that function
+ *   b2g_ntt                <- Radix2EvaluationDomain::{fft,ifft}_in_place (ark-poly 0.5.0) as used at qap.rs:60-81
+ *   b2g_prove_partial / b2g_prove_finish : the same proof split for base-range sharding over several GPUs
+ *   b2g_fixed_base_g1/g2   <- the batch fixed-base multiplications of generate_random_parameters_with_reduction
+ *                             (tests/groth16.rs:25); used to manufacture synthetic proving keys
+ *
+ * Conventions
+ *   - every function returns 0 (B2G_OK) or a negative error code; b2g_last_error() gives a thread-local message.
+ *     No exception or unwinding ever crosses this boundary.
+ *   - field elements are 32 bytes, little-endian.  "mont" = Montgomery form with R = 2^256 exactly as a .zkey stores
+ *     points (src/zkey.rs:327-332) and as arkworks keeps Fp256 in memory; "canon" = the plain integer.
+ *   - G1 affine = x||y (64 B, mont), G2 affine = x.c0||x.c1||y.c0||y.c1 (128 B, mont); all-zero bytes = infinity
+ *     (src/zkey.rs:340-360).
+ *   - host pointers are only read/written during the call; handles own all device memory.
+ *   - one proof in flight per b2g_ctx (a ctx is not thread-safe); create one ctx per GPU.
+ *   - there is no CPU fallback: without a CUDA device every call fails with B2G_E_DEVICE.
+ */
+#ifndef B2GROTH_H
+#define B2GROTH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B2G_API __attribute__((visibility("default")))
+#else
+#define B2G_API
+#endif
+
+#define B2G_OK 0
+#define B2G_E_DOMAIN (-1) /* evaluation domain too large: SynthesisError::PolynomialDegreeTooLarge (qap.rs:31,66) */
+#define B2G_E_SHAPE (-2)  /* inconsistent sizes / null pointers */
+#define B2G_E_DEVICE (-3) /* CUDA failure, or no CUDA device */
+#define B2G_E_INPUT (-4)  /* malformed input data */
+
+typedef struct b2g_ctx b2g_ctx;
+typedef struct b2g_pk b2g_pk;
+typedef struct b2g_mat b2g_mat;
+
+/* Proving key as read_zkey() produces it (src/zkey.rs:121-130); every pointer is a HOST pointer. */
+typedef struct {
+    uint32_t n_vars;          /* zkey header nVars  (src/zkey.rs:303) */
+    uint32_t n_public;        /* zkey header nPublic */
+    uint32_t domain_size;     /* zkey header domainSize = number of H bases */
+    uint32_t reserved;
+    const void* alpha_g1;     /* 64 B  */
+    const void* beta_g1;      /* 64 B  */
+    const void* delta_g1;     /* 64 B  */
+    const void* beta_g2;      /* 128 B */
+    const void* delta_g2;     /* 128 B */
+    const void* a_query;      /* n_vars G1                 zkey section 5 */
+    const void* b_g1_query;   /* n_vars G1                 zkey section 6 */
+    const void* b_g2_query;   /* n_vars G2                 zkey section 7 */
+    const void* l_query;      /* n_vars - n_public - 1 G1  zkey section 8 */
+    const void* h_query;      /* domain_size G1            zkey section 9 */
+} b2g_pk_desc;
+
+/* ConstraintMatrices<Fr> a and b (src/zkey.rs:181-193) in CSR form; c is empty on the zkey route.  Values mont. */
+typedef struct {
+    uint32_t num_constraints; /* m: rows kept (src/zkey.rs:171-175) */
+    uint32_t num_inputs;      /* num_instance_variables = n_public + 1 (src/zkey.rs:182) */
+    uint32_t n_vars;          /* length of the full assignment */
+    uint32_t reserved;
+    const uint32_t* a_rowptr; /* m + 1 */
+    const uint32_t* a_col;
+    const void* a_val;        /* nnz x 32 B mont */
+    const uint32_t* b_rowptr;
+    const uint32_t* b_col;
+    const void* b_val;
+} b2g_mat_desc;
+
+B2G_API const char* b2g_last_error(void);
+B2G_API int b2g_version(void);
+B2G_API int b2g_device_count(int* count);
+
+/* One context per GPU.  shard_rank / shard_count partition every query's base range (rank r of R owns the r-th
+ * contiguous slice); use 0 / 1 for a whole-proof context. */
+B2G_API int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out);
+B2G_API int b2g_ctx_destroy(b2g_ctx* ctx);
+
+B2G_API int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* desc, b2g_pk** out);
+B2G_API int b2g_pk_free(b2g_pk* pk);
+B2G_API int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* desc, b2g_mat** out);
+B2G_API int b2g_matrices_free(b2g_mat* mat);
+
+/* h = witness map; w_mont = n_vars x 32 B (host); h_out = domain x 32 B mont, natural order (host). */
+B2G_API int b2g_witness_map(b2g_ctx* ctx, b2g_mat* mat, const void* w_mont, void* h_out, uint32_t* domain_size_out);
+
+/* 256-byte proof: A.x A.y B.x.c0 B.x.c1 B.y.c0 B.y.c1 C.x C.y, canon little-endian; infinity = zeros.
+ * r, s canon (32 B each).  Requires shard_count == 1. */
+B2G_API int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont,
+              uint8_t proof_out[256]);
+
+/* Sharded proof.  partial_out (768 B, host or device-accessible host memory) = this rank's partial MSM results
+ * [H, L, A, B1] as G1 XYZZ (128 B each) followed by B2 as G2 XYZZ (256 B), mont.  b2g_prove_finish folds
+ * shard_count partials in rank order and assembles the proof; every rank obtains identical bytes. */
+#define B2G_PARTIAL_BYTES 768
+B2G_API int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont, void* partial_out);
+B2G_API int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int count, const void* r_canon,
+                     const void* s_canon, uint8_t proof_out[256]);
+
+/* Kernel-level entry points (parity tests, benchmarks). All pointers host. */
+B2G_API int b2g_msm_g1(b2g_ctx* ctx, const void* bases, const void* scalars, size_t n, int scalars_mont, void* out_xy_mont);
+B2G_API int b2g_msm_g2(b2g_ctx* ctx, const void* bases, const void* scalars, size_t n, int scalars_mont, void* out_xy_mont);
+B2G_API int b2g_ntt(b2g_ctx* ctx, void* data_mont, int log_n, int inverse);
+B2G_API int b2g_fixed_base_g1(b2g_ctx* ctx, const void* scalars_canon, size_t n, void* out_affine_mont);
+B2G_API int b2g_fixed_base_g2(b2g_ctx* ctx, const void* scalars_canon, size_t n, void* out_affine_mont);
+
+/* Element-wise device arithmetic, for unit parity tests of the field / group layers.
+ * op: 0 fq_mul, 1 fq_add, 2 fq_sub, 3 fr_mul, 4 fr_add, 5 fr_sub, 6 fq_inv, 7 fr_inv (b ignored),
+ *     8 g1_add (a, b, out = n x 64 B affine), 9 g2_add (n x 128 B), 10 g1_dbl, 11 g2_dbl (b ignored). */
+B2G_API int b2g_test_op(b2g_ctx* ctx, int op, const void* a, const void* b, size_t n, void* out);
+
+/* Timing of the last b2g_prove / b2g_prove_partial on this ctx, CUDA-event milliseconds:
+ * [0] h2d witness, [1] witness map, [2] msm H, [3] msm L, [4] msm A, [5] msm B1, [6] msm B2, [7] glue + d2h,
+ * [8] whole call (first event to last event). */
+B2G_API int b2g_last_timings(b2g_ctx* ctx, float out_ms[16]);
+
+/* Benchmark helper: the device-resident part of a proof (witness already in HBM from the last b2g_prove call):
+ * runs witness map + 5 MSMs + glue `iters` times and returns the average CUDA-event milliseconds. */
+B2G_API int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* avg_ms);
+/* number of kernel launches issued by this library on the ctx since creation */
+B2G_API int b2g_launch_count(b2g_ctx* ctx, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2GROTH_H */

@@ -1,0 +1,38 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope='session')
+def golden():
+    return json.load(open(os.path.join(GOLDEN, 'golden_vectors.json')))
+
+
+@pytest.fixture(scope='session')
+def test_zkey_bytes():
+    return open(os.path.join(GOLDEN, 'test.zkey'), 'rb').read()
+
+
+@pytest.fixture(scope='session')
+def complex_zkey_bytes():
+    return open(os.path.join(GOLDEN, 'complex-circuit-10000-10000.zkey'), 'rb').read()
+
+
+@pytest.fixture(scope='session')
+def ctx():
+    """A real device context.  GPU tests never skip and never fall back: no CUDA => failure."""
+    from circom_compat_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()

@@ -1,0 +1,250 @@
+"""GPU parity tests: every call goes through the C ABI (libb2groth.so) and is compared bit-for-bit with the oracle
+(oracle/cref.c restatement, oracle/pyref.py big-int) on the same inputs.  Integer work => exact equality."""
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import cref as c
+from oracle import pyref as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_fe(rng, n, mod, extra=()):
+    vals = [rng.randrange(mod) for _ in range(n)] + list(extra)
+    return vals
+
+
+# ------------------------------------------------------------------------------------------------ field layer
+@pytest.mark.parametrize('field', ['fq', 'fr'])
+def test_field_ops(ctx, field):
+    rng = random.Random(11)
+    mod = o.Q_MOD if field == 'fq' else o.R_MOD
+    to_m = c.fq_to_mont if field == 'fq' else c.fr_to_mont
+    from_m = c.fq_from_mont if field == 'fq' else c.fr_from_mont
+    base = 0 if field == 'fq' else 3
+    edge = [0, 1, 2, mod - 1, mod - 2, (1 << 253), (1 << 254) % mod, mod >> 1]
+    a = _rand_fe(rng, 3000, mod, edge + edge)
+    b = _rand_fe(rng, 3000, mod, edge + edge[::-1])
+    am, bm = to_m(c.ints_to_limbs(a)), to_m(c.ints_to_limbs(b))
+    assert c.limbs_to_ints(from_m(ctx.test_op(base + 0, am, bm))) == [x * y % mod for x, y in zip(a, b)]
+    assert c.limbs_to_ints(from_m(ctx.test_op(base + 1, am, bm))) == [(x + y) % mod for x, y in zip(a, b)]
+    assert c.limbs_to_ints(from_m(ctx.test_op(base + 2, am, bm))) == [(x - y) % mod for x, y in zip(a, b)]
+    nz = [x for x in a if x][:64]
+    inv = ctx.test_op(6 if field == 'fq' else 7, to_m(c.ints_to_limbs(nz)))
+    assert c.limbs_to_ints(from_m(inv)) == [pow(x, -1, mod) for x in nz]
+
+
+def test_group_ops(ctx):
+    rng = random.Random(5)
+    n = 200
+    ka = [rng.randrange(1, o.R_MOD) for _ in range(n)]
+    kb = [rng.randrange(1, o.R_MOD) for _ in range(n)]
+    kb[0] = ka[0]                      # P + P  -> doubling branch
+    kb[1] = o.R_MOD - ka[1]            # P + (-P) -> infinity
+    pa, pb = c.fixed_base_g1(c.ints_to_limbs(ka)), c.fixed_base_g1(c.ints_to_limbs(kb))
+    pa[2] = 0; pb[3] = 0; pa[4] = 0; pb[4] = 0      # infinities on either / both sides
+    exp = np.stack([c.add_g1(x, y) for x, y in zip(pa, pb)])
+    assert np.array_equal(ctx.test_op(8, pa, pb), exp)          # full XYZZ addition
+    assert np.array_equal(ctx.test_op(12, pa, pb), exp)         # mixed addition
+    assert np.array_equal(ctx.test_op(10, pa), np.stack([c.add_g1(x, x) for x in pa]))
+    qa, qb = c.fixed_base_g2(c.ints_to_limbs(ka[:60])), c.fixed_base_g2(c.ints_to_limbs(kb[:60]))
+    qa[2] = 0; qb[3] = 0
+    exp2 = np.stack([c.add_g2(x, y) for x, y in zip(qa, qb)])
+    assert np.array_equal(ctx.test_op(9, qa, qb), exp2)
+    assert np.array_equal(ctx.test_op(13, qa, qb), exp2)
+    assert np.array_equal(ctx.test_op(11, qa), np.stack([c.add_g2(x, x) for x in qa]))
+
+
+def test_fixed_base(ctx):
+    rng = random.Random(2)
+    ks = [0, 1, 2, o.R_MOD - 1] + [rng.randrange(o.R_MOD) for _ in range(300)]
+    lim = c.ints_to_limbs(ks)
+    assert np.array_equal(ctx.fixed_base_g1(lim), c.fixed_base_g1(lim))
+    assert np.array_equal(ctx.fixed_base_g2(lim[:80]), c.fixed_base_g2(lim[:80]))
+
+
+# ------------------------------------------------------------------------------------------------ NTT
+@pytest.mark.parametrize('log_n', [1, 2, 3, 7, 10, 11, 14, 16])
+def test_ntt_plain(ctx, log_n):
+    rng = np.random.default_rng(log_n)
+    n = 1 << log_n
+    vals = c.fr_to_mont(c.ints_to_limbs([int(x) for x in rng.integers(0, 2**62, n)]))      # any residues will do
+    vals = c.fr_mul(vals, vals[::-1].copy())                                                 # spread over the field
+    assert np.array_equal(ctx.ntt(vals), c.ntt(vals))
+    assert np.array_equal(ctx.ntt(vals, inverse=True), c.ntt(vals, inverse=True))
+
+
+def test_ntt_linearity_large(ctx):
+    # size-independent property at the headline size: NTT(a + b) = NTT(a) + NTT(b), iNTT(NTT(a)) = a
+    log_n = 20
+    n = 1 << log_n
+    rng = np.random.default_rng(99)
+    raw = rng.integers(0, 2**63, (2, n, 4), dtype=np.uint64); raw[..., 3] &= (1 << 60) - 1   # < r
+    a, b = raw[0], raw[1]
+    fa, fb = ctx.ntt(a), ctx.ntt(b)
+    s = ctx.test_op(4, a, b)
+    assert np.array_equal(ctx.ntt(s), ctx.test_op(4, fa, fb))
+    assert np.array_equal(ctx.ntt(fa, inverse=True), a)
+
+
+# ------------------------------------------------------------------------------------------------ MSM
+def _msm_case(rng, n, dist):
+    ks = [rng.randrange(1, o.R_MOD) for _ in range(n)]
+    if dist == 'uniform':
+        sc = [rng.randrange(o.R_MOD) for _ in range(n)]
+    elif dist == 'circomlike':      # 60 % bits, 20 % small, 20 % wide
+        sc = [rng.randrange(2) if (u := rng.random()) < 0.6 else (rng.randrange(1 << 32) if u < 0.8 else rng.randrange(o.R_MOD)) for _ in range(n)]
+    elif dist == 'ones':
+        sc = [1] * n
+    elif dist == 'same':
+        v = rng.randrange(o.R_MOD); sc = [v] * n
+    else:
+        sc = [0] * n
+    return ks, sc
+
+
+@pytest.mark.parametrize('n,dist', [(1, 'uniform'), (2, 'uniform'), (3, 'ones'), (33, 'uniform'), (257, 'zeros'), (1000, 'circomlike'),
+                                    (4096, 'uniform'), (5000, 'same'), (70000, 'uniform'), (70000, 'circomlike'), (70000, 'ones')])
+def test_msm_g1(ctx, n, dist):
+    rng = random.Random(n * 7 + len(dist))
+    ks, sc = _msm_case(rng, n, dist)
+    bases = c.fixed_base_g1(c.ints_to_limbs(ks))
+    if n > 40:
+        bases[5] = 0; bases[9] = bases[8]; sc[8] = 5; sc[9] = o.R_MOD - 5; sc[0] = 0; sc[1] = 1; sc[2] = o.R_MOD - 1
+    scl = c.ints_to_limbs(sc)
+    exp = c.msm_g1(bases, scl)
+    assert np.array_equal(ctx.msm_g1(bases, scl), exp)
+    assert np.array_equal(ctx.msm_g1(bases, c.fr_to_mont(scl), scalars_mont=True), exp)
+
+
+@pytest.mark.parametrize('n,dist', [(1, 'uniform'), (3, 'ones'), (300, 'circomlike'), (5000, 'uniform'), (40000, 'circomlike')])
+def test_msm_g2(ctx, n, dist):
+    rng = random.Random(n * 13 + len(dist))
+    ks, sc = _msm_case(rng, n, dist)
+    bases = c.fixed_base_g2(c.ints_to_limbs(ks))
+    if n > 40:
+        bases[5] = 0; bases[9] = bases[8]; sc[8] = 5; sc[9] = o.R_MOD - 5
+    scl = c.ints_to_limbs(sc)
+    assert np.array_equal(ctx.msm_g2(bases, scl), c.msm_g2(bases, scl))
+
+
+def test_msm_small_chunks_exercise_fragments(ctx, monkeypatch):
+    # tiny runs (B2G_MSM_CHUNK) force buckets to straddle many threads, including the whole-CTA fold path
+    rng = random.Random(77)
+    n = 6000
+    ks, sc = _msm_case(rng, n, 'circomlike')
+    bases = c.fixed_base_g1(c.ints_to_limbs(ks)); scl = c.ints_to_limbs(sc)
+    exp = c.msm_g1(bases, scl)
+    for chunk in ('1', '2', '3', '7'):
+        monkeypatch.setenv('B2G_MSM_CHUNK', chunk)
+        assert np.array_equal(ctx.msm_g1(bases, scl), exp), chunk
+
+
+def test_msm_truncation_rule(ctx):
+    rng = random.Random(3)
+    bases = c.fixed_base_g1(c.ints_to_limbs([rng.randrange(1, o.R_MOD) for _ in range(50)]))
+    sc = c.ints_to_limbs([rng.randrange(o.R_MOD) for _ in range(31)])
+    assert np.array_equal(ctx.msm_g1(bases, sc), c.msm_g1(bases[:31], sc))
+    assert not ctx.msm_g1(bases[:0], sc[:0]).any()
+
+
+# ------------------------------------------------------------------------------------------------ witness map + proofs
+def test_witness_map_and_proofs_test_zkey(ctx, golden, test_zkey_bytes):
+    # verify_proof_with_zkey_without_r1cs (src/zkey.rs:875-919) with pinned r, s
+    from circom_compat_b200 import read_zkey, Groth16, CircomReduction, fr_to_mont, fr_from_mont
+    pk, cm = read_zkey(test_zkey_bytes)
+    g = golden['test_zkey']
+    w = [int(x) for x in g['witness']]
+    wm = fr_to_mont(w)
+    h = CircomReduction.witness_map_from_matrices(cm, cm.num_instance_variables, cm.num_constraints, wm, ctx)
+    assert [str(x) for x in fr_from_mont(h)] == g['h']
+    z = o.read_zkey(test_zkey_bytes)
+    for i, case in enumerate(g['proofs']):
+        p = Groth16.create_proof_with_reduction_and_matrices(pk, int(case['r']), int(case['s']), cm, cm.num_instance_variables,
+                                                             cm.num_constraints, wm, ctx)
+        assert p.data.hex() == case['proof_hex'], i
+        if i == 0:
+            assert o.verify(z, w[1:cm.num_instance_variables], (p.a, p.b, p.c))
+
+
+def test_witness_map_and_proof_complex_zkey(ctx, golden, complex_zkey_bytes):
+    # the reference's bench workload (benches/groth16.rs:13-85): 10 000-constraint chain, domain 2^14
+    from circom_compat_b200 import read_zkey, Groth16, CircomReduction, fr_to_mont
+    pk, cm = read_zkey(complex_zkey_bytes)
+    g = golden['complex_zkey']
+    w = o.chain_witness(pk.n_vars, g['a'])
+    wm = fr_to_mont(w)
+    h = CircomReduction.witness_map_from_matrices(cm, cm.num_instance_variables, cm.num_constraints, wm, ctx)
+    hc = c.fr_from_mont(h)
+    assert [str(x) for x in c.limbs_to_ints(hc[:4])] == g['h_head']
+    assert hashlib.sha256(np.ascontiguousarray(hc).tobytes()).hexdigest() == g['h_sha256_canon_le']
+    p = Groth16.create_proof_with_reduction_and_matrices(pk, int(g['r']), int(g['s']), cm, cm.num_instance_variables, cm.num_constraints, wm, ctx)
+    assert p.data.hex() == g['proof_hex']
+
+
+def _synthetic(ctx, kind, log_n):
+    from circom_compat_b200 import synth
+    if kind == 'chain':
+        circ = synth.chain_circuit(1 << log_n); w = synth.chain_witness(1 << log_n)
+    else:
+        circ, w = synth.circomlike_circuit(log_n)
+    pk, td = synth.setup(ctx, circ)
+    return circ, w, pk, td
+
+
+def _oracle_key(pk, cm):
+    za = dict(n_vars=pk.n_vars, n_public=pk.n_public, domain_size=pk.domain_size, num_constraints=cm.num_constraints, a_csr=cm.a, b_csr=cm.b)
+    for name in ('alpha_g1', 'beta_g1', 'delta_g1', 'beta_g2', 'delta_g2', 'a_query', 'b_g1_query', 'b_g2_query', 'l_query', 'h_query'):
+        za[name] = np.ascontiguousarray(getattr(pk, name), dtype=np.uint64)
+    return za
+
+
+@pytest.mark.parametrize('kind,log_n', [('chain', 12), ('circomlike', 13), ('chain', 16)])
+def test_synthetic_proof_vs_oracle_and_trapdoor(ctx, kind, log_n):
+    # BASELINE.json config 2 (2^16, MSM + NTT correctness vs CPU) and smaller shapes
+    from circom_compat_b200 import Groth16, CircomReduction, fr_to_mont, fr_from_mont, synth
+    circ, w, pk, td = _synthetic(ctx, kind, log_n)
+    cm = circ.matrices()
+    # spot-check GPU-generated bases against the oracle's fixed-base multiplication
+    rng = random.Random(log_n)
+    for i in [0, 1, pk.n_vars - 1] + [rng.randrange(pk.n_vars) for _ in range(20)]:
+        assert np.array_equal(pk.a_query[i], c.fixed_base_g1(c.ints_to_limbs([td.a_t[i]]))[0])
+        assert np.array_equal(pk.b_g2_query[i], c.fixed_base_g2(c.ints_to_limbs([td.b_t[i]]))[0])
+    wm = fr_to_mont(w)
+    r, s = rng.randrange(o.R_MOD), rng.randrange(o.R_MOD)
+    h = CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    p = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    pb, h_ref = c.prove(_oracle_key(pk, cm), r, s, wm, want_h=True)
+    assert np.array_equal(h, h_ref)
+    assert p.data == pb
+    da, db, dc = synth.expected_proof_dlogs(td, w, fr_from_mont(h), r, s, circ.num_inputs)
+    assert o.G1.mul(o.G1_GEN, da) == p.a and o.G2.mul(o.G2_GEN, db) == p.b and o.G1.mul(o.G1_GEN, dc) == p.c
+
+
+def test_sharded_proof_equals_whole_proof(golden, complex_zkey_bytes):
+    # base-range sharding on one device: 3 shard contexts, partials folded in rank order
+    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, Context
+    pk, cm = read_zkey(complex_zkey_bytes)
+    g = golden['complex_zkey']
+    wm = fr_to_mont(o.chain_witness(pk.n_vars, g['a']))
+    parts, ctxs = [], []
+    for rank in range(3):
+        cx = Context(0, rank, 3); ctxs.append(cx)
+        parts.append(Groth16.prove_partial(pk, cm, wm, cx))
+    p = Groth16.prove_finish(pk, np.stack(parts), int(g['r']), int(g['s']), ctxs[1])
+    assert p.data.hex() == g['proof_hex']
+    for cx in ctxs:
+        cx.close()
+
+
+def test_error_behaviour(ctx, test_zkey_bytes):
+    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, B2gError
+    pk, cm = read_zkey(test_zkey_bytes)
+    with pytest.raises(ValueError):
+        Groth16.create_proof_with_reduction_and_matrices(pk, 1, 1, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont([1, 2, 3]), ctx)
+    with pytest.raises(B2gError):
+        ctx.ntt(np.zeros((1 << 3, 4), dtype=np.uint64)[:0].reshape(0, 4)) if False else ctx.test_op(99, np.zeros((1, 4), dtype=np.uint64))

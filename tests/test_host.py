@@ -1,0 +1,101 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, fails loudly without a GPU,
+the host zkey reader produces the reference's structures, and the synthetic setup is a valid Groth16 key."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import cref as c
+from oracle import pyref as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    from circom_compat_b200 import _native as N
+    hdr = open(os.path.join(ROOT, 'include', 'b2groth.h')).read()
+    declared = set(re.findall(r'B2G_API\s+[\w\s\*]*?\b(b2g_\w+)\s*\(', hdr))
+    assert len(declared) >= 20
+    L = N.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(N.EXPORTS)
+    assert L.b2g_version() == 1
+
+
+@pytest.mark.skipif(_has_cuda(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from circom_compat_b200 import Context, B2gError
+    with pytest.raises(B2gError) as e:
+        Context(0)
+    assert e.value.code == -3
+
+
+def test_read_zkey_matches_oracle_reader(test_zkey_bytes, complex_zkey_bytes):
+    from circom_compat_b200 import read_zkey
+    for data in (test_zkey_bytes, complex_zkey_bytes):
+        pk, cm = read_zkey(data)
+        za = c.zkey_arrays(data)
+        assert (pk.n_vars, pk.n_public, pk.domain_size) == (za['n_vars'], za['n_public'], za['domain_size'])
+        assert cm.num_constraints == za['num_constraints'] and cm.num_instance_variables == za['n_public'] + 1
+        assert cm.num_witness_variables == za['n_vars'] - za['n_public'] - 1 and cm.c_num_non_zero == 0
+        for name in ('alpha_g1', 'beta_g1', 'delta_g1', 'beta_g2', 'delta_g2', 'a_query', 'b_g1_query', 'b_g2_query', 'l_query', 'h_query'):
+            assert np.array_equal(getattr(pk, name), za[name]), name
+        for i in range(3):
+            assert np.array_equal(cm.a[i], za['a_csr'][i]) and np.array_equal(cm.b[i], za['b_csr'][i])
+        assert cm.a_num_non_zero == len(za['a_csr'][1]) and cm.b_num_non_zero == len(za['b_csr'][1])
+
+
+def test_read_zkey_rejects_garbage():
+    from circom_compat_b200 import read_zkey
+    with pytest.raises(ValueError):
+        read_zkey(b'r1cs' + bytes(64))
+
+
+def test_montgomery_helpers_roundtrip():
+    from circom_compat_b200 import fr_to_mont, fr_from_mont
+    vals = [0, 1, 33, o.R_MOD - 1, 12345678901234567890123456789]
+    m = fr_to_mont(vals)
+    assert fr_from_mont(m) == vals
+    assert np.array_equal(m, c.fr_to_mont(c.ints_to_limbs(vals)))
+
+
+class _CpuFixedBase:
+    """stands in for Context in synth.setup on a CPU-only box (group elements from the oracle)"""
+    def fixed_base_g1(self, s): return c.fixed_base_g1(s)
+    def fixed_base_g2(self, s): return c.fixed_base_g2(s)
+
+
+@pytest.mark.parametrize('kind', ['chain', 'circomlike'])
+def test_synthetic_setup_is_a_valid_groth16_key(kind, tmp_path):
+    from circom_compat_b200 import synth, read_zkey, fr_to_mont, fr_from_mont
+    if kind == 'chain':
+        circ = synth.chain_circuit(64); w = synth.chain_witness(64)
+    else:
+        circ, w = synth.circomlike_circuit(9)
+    pk, td = synth.setup(_CpuFixedBase(), circ)
+    assert td.h_t == o.h_query_scalars(circ.domain_size - 1, td.tau, pow(td.delta, -1, o.R_MOD))   # qap.rs:90-105 literally
+    path = str(tmp_path / 'syn.zkey')
+    synth.write_zkey(path, pk, circ)
+    data = open(path, 'rb').read()
+    za = c.zkey_arrays(data)
+    r, s = 0x1234567890abcdef, 0xfedcba0987654321
+    pb, h = c.prove(za, r, s, fr_to_mont(w), want_h=True)
+    v = [int.from_bytes(pb[i:i + 32], 'little') for i in range(0, 256, 32)]
+    proof = ((v[0], v[1]), ((v[2], v[3]), (v[4], v[5])), (v[6], v[7]))
+    z = o.read_zkey(data)
+    assert o.verify(z, w[1:circ.num_inputs], proof)
+    da, db, dc = synth.expected_proof_dlogs(td, w, fr_from_mont(h), r, s, circ.num_inputs)
+    assert o.G1.mul(o.G1_GEN, da) == proof[0] and o.G2.mul(o.G2_GEN, db) == proof[1] and o.G1.mul(o.G1_GEN, dc) == proof[2]
+    pk2, cm2 = read_zkey(data)
+    assert pk2.n_vars == circ.n_vars and cm2.num_constraints == circ.num_constraints

@@ -1,0 +1,150 @@
+"""CPU tests of the oracle itself (oracle/pyref.py big-int, oracle/cref.c restatement) against the reference's
+golden vectors and KATs.  Mirrors the unit tests of /root/reference/src/zkey.rs:465-543 and the end-to-end
+`verified` assertions of src/zkey.rs:846-919."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle import cref as c
+from oracle import pyref as o
+
+
+def _limbs_rand(rng, n, mod):
+    return c.ints_to_limbs([rng.randrange(mod) for _ in range(n)])
+
+
+def test_kat_field_and_generators(golden):
+    # can_deser_fq / can_deser_g1 / can_deser_g2 (src/zkey.rs:465-517): snarkjs Montgomery encodings of one / G1 / G2
+    assert o._fq_from_mont(bytes(golden['kat_fq_one'])) == 1
+    assert o._g1_from(bytes(golden['kat_g1_one'])) == o.G1_GEN
+    assert o._g2_from(bytes(golden['kat_g2_one'])) == o.G2_GEN
+    # the C oracle decodes the same bytes
+    one = c.fq_from_mont(np.frombuffer(bytes(golden['kat_fq_one']), dtype='<u8'))
+    assert c.limbs_to_ints(one) == [1]
+    g1 = c.fq_from_mont(np.frombuffer(bytes(golden['kat_g1_one']), dtype='<u8'))
+    assert c.limbs_to_ints(g1) == [1, 2]
+
+
+def test_zkey_header_and_sections(test_zkey_bytes):
+    # src/zkey.rs:519-543: n_vars = 4, n_public = 1, domain_size = 4; section sizes
+    z = o.read_zkey(test_zkey_bytes)
+    assert (z.n_vars, z.n_public, z.domain_size) == (4, 1, 4)
+    assert len(z.a_query) == 4 and len(z.b_g2_query) == 4 and len(z.l_query) == 2 and len(z.h_query) == 4 and len(z.ic) == 2
+    assert z.num_constraints == 1 and z.num_inputs == 2
+    assert z.mat_a == [[(o.R_MOD - 1, 2)]] and z.mat_b == [[(1, 3)]]      # coefficients decode to -1 / +1
+
+
+def test_verification_key_json(test_zkey_bytes):
+    # deser_vk (src/zkey.rs:765-779) against test-vectors/verification_key.json
+    import json, os
+    vk = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'verification_key.json')))
+    z = o.read_zkey(test_zkey_bytes)
+    assert z.alpha_g1 == (int(vk['vk_alpha_1'][0]), int(vk['vk_alpha_1'][1]))
+    def g2(v): return ((int(v[0][0]), int(v[0][1])), (int(v[1][0]), int(v[1][1])))
+    assert z.beta_g2 == g2(vk['vk_beta_2']) and z.gamma_g2 == g2(vk['vk_gamma_2']) and z.delta_g2 == g2(vk['vk_delta_2'])
+    assert z.ic == [(int(p[0]), int(p[1])) for p in vk['IC']]
+
+
+def test_pyref_matches_golden_and_verifies(golden, test_zkey_bytes):
+    z = o.read_zkey(test_zkey_bytes)
+    g = golden['test_zkey']
+    w = [int(x) for x in g['witness']]
+    assert [str(x) for x in o.witness_map_from_matrices(z.mat_a, z.mat_b, z.num_inputs, z.num_constraints, w)] == g['h']
+    case = g['proofs'][0]
+    A, B, C = o.prove(z, int(case['r']), int(case['s']), w)
+    assert o.proof_to_bytes(A, B, C).hex() == case['proof_hex']
+    assert o.verify(z, w[1:z.num_inputs], (A, B, C))                       # verify_proof_with_zkey_* assert `verified`
+    assert not o.verify(z, [34], (A, B, C))                                # tests/groth16.rs:42-74 wrong public input
+
+
+def test_cref_matches_golden_small(golden, test_zkey_bytes):
+    za = c.zkey_arrays(test_zkey_bytes)
+    g = golden['test_zkey']
+    wm = c.fr_to_mont(c.ints_to_limbs([int(x) for x in g['witness']]))
+    for case in g['proofs']:
+        pb, h = c.prove(za, int(case['r']), int(case['s']), wm, want_h=True)
+        assert pb.hex() == case['proof_hex']
+        assert [str(x) for x in c.limbs_to_ints(c.fr_from_mont(h))] == g['h']
+
+
+def test_cref_matches_golden_complex(golden, complex_zkey_bytes):
+    za = c.zkey_arrays(complex_zkey_bytes)
+    assert (za['n_vars'], za['domain_size'], za['num_constraints']) == (10002, 16384, 10000)
+    g = golden['complex_zkey']
+    w = o.chain_witness(za['n_vars'], g['a'])
+    wm = c.fr_to_mont(c.ints_to_limbs(w))
+    pb, h = c.prove(za, int(g['r']), int(g['s']), wm, want_h=True)
+    hc = c.fr_from_mont(h)
+    assert [str(x) for x in c.limbs_to_ints(hc[:4])] == g['h_head']
+    assert hashlib.sha256(np.ascontiguousarray(hc).tobytes()).hexdigest() == g['h_sha256_canon_le']
+    assert pb.hex() == g['proof_hex']
+
+
+def test_cref_field_vs_bigint():
+    rng = random.Random(1)
+    a = [rng.randrange(o.Q_MOD) for _ in range(200)] + [0, 1, o.Q_MOD - 1]
+    b = [rng.randrange(o.Q_MOD) for _ in range(200)] + [o.Q_MOD - 1, o.Q_MOD - 1, o.Q_MOD - 1]
+    am, bm = c.fq_to_mont(c.ints_to_limbs(a)), c.fq_to_mont(c.ints_to_limbs(b))
+    assert c.limbs_to_ints(c.fq_from_mont(c.fq_mul(am, bm))) == [x * y % o.Q_MOD for x, y in zip(a, b)]
+    a = [rng.randrange(o.R_MOD) for _ in range(200)]
+    b = [rng.randrange(o.R_MOD) for _ in range(200)]
+    am, bm = c.fr_to_mont(c.ints_to_limbs(a)), c.fr_to_mont(c.ints_to_limbs(b))
+    assert c.limbs_to_ints(c.fr_from_mont(c.fr_mul(am, bm))) == [x * y % o.R_MOD for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize('log_n', [1, 2, 5, 8])
+def test_cref_ntt_vs_bigint(log_n):
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    v = [rng.randrange(o.R_MOD) for _ in range(n)]
+    vm = c.fr_to_mont(c.ints_to_limbs(v))
+    fwd = c.limbs_to_ints(c.fr_from_mont(c.ntt(vm)))
+    assert fwd == o.fft(list(v))
+    # definition check: X[k] = sum v[j] w^(jk)
+    w = o.root_of_unity(n)
+    assert fwd[1 % n] == sum(v[j] * pow(w, j * (1 % n), o.R_MOD) for j in range(n)) % o.R_MOD
+    inv = c.limbs_to_ints(c.fr_from_mont(c.ntt(c.ntt(vm), inverse=True)))
+    assert inv == v
+
+
+def _rand_points_g1(rng, n):
+    return c.fixed_base_g1(c.ints_to_limbs([rng.randrange(1, o.R_MOD) for _ in range(n)]))
+
+
+def test_cref_msm_vs_bigint_with_edge_cases():
+    rng = random.Random(7)
+    n = 70
+    ks = [rng.randrange(1, o.R_MOD) for _ in range(n)]
+    bases = c.fixed_base_g1(c.ints_to_limbs(ks))
+    bases[5] = 0                                   # a point at infinity (zkey convention: zeros)
+    bases[9] = bases[8]                            # repeated base
+    sc = [rng.randrange(o.R_MOD) for _ in range(n)]
+    sc[0] = 0; sc[1] = 1; sc[2] = o.R_MOD - 1; sc[8] = 5; sc[9] = o.R_MOD - 5   # P*5 + P*(-5) cancels
+    got = c.msm_g1(bases, c.ints_to_limbs(sc))
+    pts = [None if not b.any() else tuple(c.limbs_to_ints(c.fq_from_mont(b))) for b in bases]
+    exp = o.G1.msm(pts, sc)
+    assert tuple(c.limbs_to_ints(c.fq_from_mont(got))) == exp
+    # G2
+    ks2 = [rng.randrange(1, o.R_MOD) for _ in range(20)]
+    b2 = c.fixed_base_g2(c.ints_to_limbs(ks2))
+    sc2 = [rng.randrange(o.R_MOD) for _ in range(20)]
+    got2 = c.limbs_to_ints(c.fq_from_mont(c.msm_g2(b2, c.ints_to_limbs(sc2))))
+    exp2 = o.G2.mul(o.G2_GEN, sum(a * b for a, b in zip(ks2, sc2)) % o.R_MOD)
+    assert ((got2[0], got2[1]), (got2[2], got2[3])) == exp2
+    # fixed-base spot check
+    assert tuple(c.limbs_to_ints(c.fq_from_mont(bases[3]))) == o.G1.mul(o.G1_GEN, ks[3])
+
+
+def test_msm_truncates_to_shorter_side():
+    # msm_bigint pairs min(len(bases), len(scalars)) terms
+    rng = random.Random(3)
+    bases = _rand_points_g1(rng, 10)
+    sc = c.ints_to_limbs([rng.randrange(o.R_MOD) for _ in range(6)])
+    assert np.array_equal(c.msm_g1(bases, sc), c.msm_g1(bases[:6], sc))
+
+
+def test_witness_map_domain_too_large():
+    with pytest.raises(ValueError):
+        o.domain_size_for((1 << 28) + 1)
