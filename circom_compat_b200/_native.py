@@ -36,7 +36,7 @@ class MatDesc(C.Structure):
 EXPORTS = ['b2g_last_error', 'b2g_version', 'b2g_device_count', 'b2g_ctx_create', 'b2g_ctx_destroy', 'b2g_pk_load', 'b2g_pk_free',
            'b2g_matrices_load', 'b2g_matrices_free', 'b2g_witness_map', 'b2g_prove', 'b2g_prove_partial', 'b2g_prove_finish',
            'b2g_msm_g1', 'b2g_msm_g2', 'b2g_ntt', 'b2g_fixed_base_g1', 'b2g_fixed_base_g2', 'b2g_test_op', 'b2g_last_timings',
-           'b2g_bench_device', 'b2g_launch_count']
+           'b2g_bench_device', 'b2g_bench_msm', 'b2g_launch_count']
 
 _lib = None
 
@@ -71,6 +71,7 @@ def lib():
         L.b2g_test_op.argtypes = [vp, i, vp, vp, sz, vp]
         L.b2g_last_timings.argtypes = [vp, vp]
         L.b2g_bench_device.argtypes = [vp, vp, vp, i, C.POINTER(C.c_float)]
+        L.b2g_bench_msm.argtypes = [vp, vp, vp, i, i, C.POINTER(C.c_float)]
         L.b2g_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.b2g_device_count.argtypes = [C.POINTER(C.c_int)]
         _lib = L

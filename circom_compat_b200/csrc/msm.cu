@@ -316,7 +316,9 @@ static void msm_run_t(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev,
     msm_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.scalars_canon, n, plan.n, plan.c, plan.nwin, s.offsets, s.cursor, s.entries);
     const uint64_t nent = (uint64_t)n * plan.nwin;
     const uint32_t nthreads = (uint32_t)((nent + chunk - 1) / chunk);
+    if (s.prof0) CUDA_CHECK(cudaEventRecord(s.prof0, st));
     msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, 0, st>>>(plan.table, s.entries, s.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
+    if (s.prof1) CUDA_CHECK(cudaEventRecord(s.prof1, st));
     msm_fold_kernel<C, F><<<(nb + 127) / 128, 128, 0, st>>>(s.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
     const size_t sh = (size_t)MSM_TREE_THREADS * ptb;
     msm_fold_big_kernel<C, F><<<64, MSM_TREE_THREADS, sh, st>>>(s.offsets, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);

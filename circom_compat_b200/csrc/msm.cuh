@@ -37,6 +37,7 @@ struct MsmScratch {                      // one per in-flight MSM
     void *frag_first = nullptr, *frag_last = nullptr, *buckets = nullptr, *partials = nullptr, *result = nullptr;
     fe* scalars_canon = nullptr;         // n canonical scalars (filled by the digit pass)
     bool g2 = false, result_owned = false;
+    cudaEvent_t prof0 = nullptr, prof1 = nullptr;   // optional: bracket the accumulate kernel (b2g_bench_msm)
 };
 
 inline int msm_pick_c(uint32_t n) {

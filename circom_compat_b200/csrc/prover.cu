@@ -558,6 +558,33 @@ int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* a
     });
 }
 
+int b2g_bench_msm(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int query, int iters, float out_ms[2]) {
+    return guarded([&] {
+        if (!out_ms || iters < 1 || query < 0 || query >= NQ) throw_error(B2G_E_SHAPE, "bad arguments");
+        check_shapes(ctx, pk, mat);
+        if (ctx->cap_w < mat->n_vars) throw_error(B2G_E_SHAPE, "no witness resident: call b2g_prove first");
+        DevGuard g(ctx->device);
+        cudaStream_t s0 = ctx->st[0];
+        MsmScratch& sc = ctx->scratch[query];
+        const fe* scalars = (query == Q_H ? ctx->d_h : ctx->d_w + pk->scalar_off[query]) + pk->lo[query];
+        std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+        for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[18], s0));
+        for (int it = 0; it < iters; it++) {
+            sc.prof0 = ev[2 * it]; sc.prof1 = ev[2 * it + 1];
+            msm_run(pk->plan[query], sc, scalars, pk->cnt[query], true, s0);
+        }
+        sc.prof0 = sc.prof1 = nullptr;
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[19], s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+        float total = 0, acc = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&total, ctx->ev_t[18], ctx->ev_t[19]));
+        for (int it = 0; it < iters; it++) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * it], ev[2 * it + 1]); acc += ms; }
+        for (auto& e : ev) cudaEventDestroy(e);
+        out_ms[0] = total / iters; out_ms[1] = acc / iters;
+    });
+}
+
 int b2g_last_timings(b2g_ctx* ctx, float out_ms[16]) {
     return guarded([&] { if (!ctx || !out_ms) throw_error(B2G_E_SHAPE, "null pointer"); memcpy(out_ms, ctx->last_ms, sizeof(ctx->last_ms)); });
 }

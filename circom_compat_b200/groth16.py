@@ -87,6 +87,18 @@ class Context:
         names = ('h2d', 'witness_map', 'msm_h', 'msm_l', 'msm_a', 'msm_b1', 'msm_b2', 'glue_d2h', 'total')
         return dict(zip(names, list(buf)[:9]))
 
+    def bench_device(self, pk, matrices, iters: int) -> float:
+        """average CUDA-event ms of witness map + 5 MSMs + glue with the witness already resident in HBM"""
+        ms = C.c_float()
+        N.check(N.lib().b2g_bench_device(self._h, self.pk_handle(pk), self.mat_handle(matrices, pk.n_vars), iters, C.byref(ms)))
+        return ms.value
+
+    def bench_msm(self, pk, matrices, query: int, iters: int):
+        """(whole-MSM ms, accumulate-kernel ms) for one query run alone: 0 H, 1 L, 2 A, 3 B1, 4 B2"""
+        out = (C.c_float * 2)()
+        N.check(N.lib().b2g_bench_msm(self._h, self.pk_handle(pk), self.mat_handle(matrices, pk.n_vars), query, iters, out))
+        return out[0], out[1]
+
     def launch_count(self) -> int:
         v = C.c_uint64()
         N.check(N.lib().b2g_launch_count(self._h, C.byref(v)))

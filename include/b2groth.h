@@ -135,6 +135,9 @@ B2G_API int b2g_last_timings(b2g_ctx* ctx, float out_ms[16]);
 /* Benchmark helper: the device-resident part of a proof (witness already in HBM from the last b2g_prove call):
  * runs witness map + 5 MSMs + glue `iters` times and returns the average CUDA-event milliseconds. */
 B2G_API int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* avg_ms);
+/* One MSM alone on the main stream, `iters` times (query: 0 H, 1 L, 2 A, 3 B1, 4 B2): out_ms[0] = average CUDA-event
+ * milliseconds of the whole MSM, out_ms[1] = of its bucket-accumulation kernel (the dominant kernel, for the roofline). */
+B2G_API int b2g_bench_msm(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int query, int iters, float out_ms[2]);
 /* number of kernel launches issued by this library on the ctx since creation */
 B2G_API int b2g_launch_count(b2g_ctx* ctx, uint64_t* count);
 
