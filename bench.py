@@ -164,23 +164,27 @@ def run_ours(args):
     from circom_compat_b200 import Context, Groth16, fr_to_mont, synth
 
     sharded = world > 1 and args.mode == 'sharded'
-    ctx = Context(local, rank if sharded else 0, world if sharded else 1)
+    inflight = 1 if sharded else max(1, args.inflight)
+    ctxs = [Context(local, rank if sharded else 0, world if sharded else 1) for _ in range(inflight)]
+    ctx = ctxs[0]
     circ, w = build_workload(args.log_n, args.workload)
     t0 = time.time()
     pk, td = synth.setup(ctx, circ)
     cm = circ.matrices()
     log(f"[bench] rank {rank}: trapdoor setup + GPU fixed-base key generation {time.time() - t0:.1f}s")
     wm_np = fr_to_mont(w)
-    pinned = torch.empty(wm_np.shape, dtype=torch.int64).pin_memory()
-    wm = pinned.numpy().view(np.uint64)
-    wm[...] = wm_np
+    pinned = [torch.empty(wm_np.shape, dtype=torch.int64).pin_memory() for _ in range(inflight)]
+    wms = [p_.numpy().view(np.uint64) for p_ in pinned]
+    for w_ in wms:
+        w_[...] = wm_np
+    wm = wms[0]
     n_vars = circ.n_vars
 
     gather_buf = torch.empty((world, 768), dtype=torch.uint8, device=f'cuda:{local}') if sharded else None
 
-    def one_proof():
+    def one_proof(i=0):
         if not sharded:
-            return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+            return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wms[i], ctxs[i])
         part = Groth16.prove_partial(pk, cm, wm, ctx)
         mine = torch.from_numpy(part).to(f'cuda:{local}', non_blocking=True)
         dist.all_gather_into_tensor(gather_buf.view(-1), mine)
@@ -213,8 +217,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_proof()
+    def run_steps(total):
+        """`total` proofs through the public API, `inflight` of them in flight (one host thread + Context each)"""
+        if inflight == 1:
+            out = None
+            for _ in range(total):
+                out = one_proof()
+            return out
+        res = [None] * inflight
+        def worker(i):
+            for _ in range(total // inflight + (1 if i < total % inflight else 0)):
+                res[i] = one_proof(i)
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(inflight)]
+        [t_.start() for t_ in ths]; [t_.join() for t_ in ths]
+        return res[0]
+
+    for i in range(1, inflight):
+        assert one_proof(i).data == proof.data
+    run_steps(max(args.warmup, inflight))
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -222,17 +242,25 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     # ---- e2e: host witness in, proof bytes out, every step
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        proof = one_proof()
+    proof = run_steps(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     launches = ctx.launch_count() - launches0
     timings = ctx.last_timings()
-    # ---- device-resident: witness already in HBM (CUDA events inside the library)
+    # ---- device-resident: witness already in HBM (CUDA events inside the library), same number in flight
     dev_ms = None
     if not sharded:
         barrier()
-        dev_ms = ctx.bench_device(pk, cm, args.steps)
+        per = [args.steps // inflight + (1 if i < args.steps % inflight else 0) for i in range(inflight)]
+        tot = [0.0] * inflight
+        def dev_worker(i):
+            if per[i]:
+                tot[i] = ctxs[i].bench_device(pk, cm, per[i]) * per[i]
+        ths = [threading.Thread(target=dev_worker, args=(i,)) for i in range(inflight)]
+        [t_.start() for t_ in ths]; [t_.join() for t_ in ths]
+        dev_ms = max(tot) / args.steps                      # ms per proof at `inflight` proofs in flight
+        barrier()
+        lat = ctx.bench_device(pk, cm, 5)                   # single proof in flight: latency
         barrier()
     clocks = sampler.stop() if rank == 0 else None
     # max over ranks
@@ -259,6 +287,9 @@ def run_ours(args):
         g2_ms, g2_acc = ctx.bench_msm(pk, cm, 4, 3)
         extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / (world if sharded else 1) * 160.0 / (g2_acc * 1e-3) / 1e9}
         extra["phase_ms_last_proof"] = timings
+        extra["in_flight"] = inflight
+        if not sharded:
+            extra["single_proof_latency_ms"] = lat
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -277,6 +308,7 @@ def run_ours(args):
 
     if rank == 0:
         cfg = workload_config(args, circ)
+        cfg["in_flight"] = inflight
         cfg["parallelism"] = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs + NCCL all-gather of 768 B partials" if sharded else f"{world} replicas")
         out = {"metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 / value * proofs_per_step, "higher_is_better": True, "scaling": "strong" if sharded or world == 1 else "weak", "vs_baseline": None,
@@ -286,7 +318,10 @@ def run_ours(args):
                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
         out.update(extra)
         print(json.dumps(out), flush=True)
-    ctx.close()
+    from circom_compat_b200 import release_all
+    release_all()
+    for c_ in ctxs:
+        c_.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -300,6 +335,7 @@ def main():
     ap.add_argument('--log-n', type=int, default=20)
     ap.add_argument('--workload', default='chain', choices=['chain', 'circomlike'])
     ap.add_argument('--mode', default='sharded', choices=['sharded', 'replicas'])
+    ap.add_argument('--inflight', type=int, default=2, help='proofs in flight per GPU (one Context + host thread each)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--skip-check', action='store_true')
     args = ap.parse_args()

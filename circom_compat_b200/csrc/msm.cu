@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const fe* __restrict__ s
 
 // ------------------------------------------------------------------------------------------------ (2) exclusive scan (one CTA)
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t nb, uint32_t* __restrict__ offsets,
-                                                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ big_count) {
+                                                        uint32_t* __restrict__ cursor) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry_s;
     const uint32_t tid = threadIdx.x, per = (nb + 1023u) / 1024u;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
     __syncthreads();
     uint32_t run = warp_sums[tid >> 5] + v - s;
     for (uint32_t j = lo; j < hi; j++) { offsets[j] = run; cursor[j] = 0; run += counts[j]; }
-    if (tid == 0) { offsets[nb] = carry_s; *big_count = 0; }
+    if (tid == 0) offsets[nb] = carry_s;
 }
 
 // ------------------------------------------------------------------------------------------------ (3) scatter
@@ -177,11 +177,17 @@ __device__ __forceinline__ typename C::Pt block_sum_points(typename C::Pt v, typ
     return sh[0];
 }
 
-constexpr int MSM_TREE_THREADS = 128;
+// Tail kernels (fold_big / reduce / sum) are latency chains on a few CTAs.  Their CTAs are kept smaller than one
+// accumulation CTA (128 threads x 126 regs for G1) so that the block scheduler can slot them in as soon as a single
+// accumulation CTA of a concurrently running query retires, instead of waiting for two slots on the same SM.
+template <class F> struct TailThreads;
+template <> struct TailThreads<Fq> { static constexpr int N = 64; };
+template <> struct TailThreads<Fq2> { static constexpr int N = 32; };
+constexpr int MSM_REDUCE_CHUNK_DEFAULT = 8;   // buckets per thread in the weighted reduction (B2G_MSM_REDUCE_CHUNK)
 
 // buckets with many fragments: one CTA each
 template <class C, class F>
-__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_fold_big_kernel(const uint32_t* __restrict__ offsets, uint32_t chunk, void* __restrict__ buckets,
+__global__ void __launch_bounds__(TailThreads<F>::N) msm_fold_big_kernel(const uint32_t* __restrict__ offsets, uint32_t chunk, void* __restrict__ buckets,
                                     const void* __restrict__ frag_first, const void* __restrict__ frag_last,
                                     const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count) {
     using Pt = typename C::Pt;
@@ -193,11 +199,11 @@ __global__ void __launch_bounds__(MSM_TREE_THREADS) msm_fold_big_kernel(const ui
         uint32_t s = offsets[b], e = offsets[b + 1];
         uint32_t t0 = s / chunk, t1 = (e - 1) / chunk;
         Pt acc = C::infinity();
-        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += MSM_TREE_THREADS) {
+        for (uint32_t t = t0 + threadIdx.x; t <= t1; t += TailThreads<F>::N) {
             Pt q = (t == t0 && s != t0 * chunk) ? pt_load<F>(frag_last, t0) : pt_load<F>(frag_first, t);
             C::add(acc, q);
         }
-        Pt r = block_sum_points<C, F, MSM_TREE_THREADS>(acc, sh);
+        Pt r = block_sum_points<C, F, TailThreads<F>::N>(acc, sh);
         if (threadIdx.x == 0) pt_store<F>(buckets, b, r);
         __syncthreads();
     }
@@ -207,15 +213,15 @@ __global__ void __launch_bounds__(MSM_TREE_THREADS) msm_fold_big_kernel(const ui
 // sum_b (b+1) * B_b.  Thread t takes buckets [t*S, (t+1)*S): running sums give A_t = sum_j (j+1) B_{tS+j} and
 // S_t = sum_j B_{tS+j}; its contribution is A_t + (t*S) * S_t (small double-and-add); a CTA tree adds them up.
 template <class C, class F>
-__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_reduce_kernel(const void* __restrict__ buckets, uint32_t nb, void* __restrict__ partials) {
+__global__ void __launch_bounds__(TailThreads<F>::N) msm_reduce_kernel(const void* __restrict__ buckets, uint32_t nb, uint32_t rchunk, void* __restrict__ partials) {
     using Pt = typename C::Pt;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     Pt* sh = reinterpret_cast<Pt*>(smem_raw);
-    const uint32_t t = blockIdx.x * MSM_TREE_THREADS + threadIdx.x;
-    const uint32_t base = t * MSM_REDUCE_CHUNK;
+    const uint32_t t = blockIdx.x * TailThreads<F>::N + threadIdx.x;
+    const uint32_t base = t * rchunk;
     Pt run = C::infinity(), acc = C::infinity();
     if (base < nb) {
-        const uint32_t cnt = min((uint32_t)MSM_REDUCE_CHUNK, nb - base);
+        const uint32_t cnt = min(rchunk, nb - base);
         for (int j = (int)cnt - 1; j >= 0; j--) {
             Pt q = pt_load<F>(buckets, base + j);
             C::add(run, q);
@@ -229,27 +235,34 @@ __global__ void __launch_bounds__(MSM_TREE_THREADS) msm_reduce_kernel(const void
             C::add(acc, m);
         }
     }
-    Pt r = block_sum_points<C, F, MSM_TREE_THREADS>(acc, sh);
+    Pt r = block_sum_points<C, F, TailThreads<F>::N>(acc, sh);
     if (threadIdx.x == 0) pt_store<F>(partials, blockIdx.x, r);
 }
 
 // sum of `count` points (count <= a few hundred) by one CTA
 template <class C, class F>
-__global__ void __launch_bounds__(MSM_TREE_THREADS) msm_sum_kernel(const void* __restrict__ pts, uint32_t count, void* __restrict__ out) {
+__global__ void __launch_bounds__(TailThreads<F>::N) msm_sum_kernel(const void* __restrict__ pts, uint32_t count, void* __restrict__ out) {
     using Pt = typename C::Pt;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     Pt* sh = reinterpret_cast<Pt*>(smem_raw);
     Pt acc = C::infinity();
-    for (uint32_t i = threadIdx.x; i < count; i += MSM_TREE_THREADS) { Pt q = pt_load<F>(pts, i); C::add(acc, q); }
-    Pt r = block_sum_points<C, F, MSM_TREE_THREADS>(acc, sh);
+    for (uint32_t i = threadIdx.x; i < count; i += TailThreads<F>::N) { Pt q = pt_load<F>(pts, i); C::add(acc, q); }
+    Pt r = block_sum_points<C, F, TailThreads<F>::N>(acc, sh);
     if (threadIdx.x == 0) pt_store<F>(out, 0, r);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    long x = strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t)x : dflt;
+}
+
 template <class C, class F>
 static void msm_build_table_t(MsmPlan& plan, const void* bases_dev, uint32_t n, cudaStream_t st) {
     const size_t aff = 2 * Bytes<F>::ELEM;
-    plan.n = n; plan.c = msm_pick_c(n ? n : 1); plan.nwin = msm_nwin(plan.c); plan.nbuckets = 1u << (plan.c - 1);
+    plan.n = n; plan.c = (int)env_u32("B2G_MSM_C", (uint32_t)msm_pick_c(n ? n : 1)); plan.nwin = msm_nwin(plan.c); plan.nbuckets = 1u << (plan.c - 1);
     if (n == 0) { plan.table = nullptr; return; }
     if ((uint64_t)n * plan.nwin >= (1ull << 31)) throw_error(B2G_E_SHAPE, "msm: n * windows exceeds 2^31 table rows");
     CUDA_CHECK(cudaMalloc(&plan.table, (size_t)n * plan.nwin * aff));
@@ -265,25 +278,21 @@ void msm_build_table(MsmPlan& plan, const void* bases_dev, uint32_t n, bool g2, 
 
 void msm_free_table(MsmPlan& plan) { if (plan.table) cudaFree(plan.table); plan.table = nullptr; }
 
-static uint32_t env_u32(const char* name, uint32_t dflt) {
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    long x = strtol(v, nullptr, 10);
-    return x > 0 ? (uint32_t)x : dflt;
-}
-
-void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2) {
+void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2, bool with_sort) {
     s.g2 = g2; s.cap_n = n; s.cap_nwin = nwin; s.cap_buckets = nbuckets;
     s.chunk = env_u32("B2G_MSM_CHUNK", 64);
     const size_t pt = (g2 ? 4 * 64 : 4 * 32);
     const size_t nent = (size_t)n * nwin;
     const size_t nchunks = (nent + s.chunk - 1) / s.chunk + 1;
-    const size_t nred = ((size_t)nbuckets + MSM_REDUCE_CHUNK - 1) / MSM_REDUCE_CHUNK;
-    const size_t npart = (nred + MSM_TREE_THREADS - 1) / MSM_TREE_THREADS;
-    CUDA_CHECK(cudaMalloc(&s.counts, (size_t)nbuckets * 4));
-    CUDA_CHECK(cudaMalloc(&s.offsets, ((size_t)nbuckets + 1) * 4));
-    CUDA_CHECK(cudaMalloc(&s.cursor, (size_t)nbuckets * 4));
-    CUDA_CHECK(cudaMalloc(&s.entries, (nent + 1) * 4));
+    s.reduce_chunk = env_u32("B2G_MSM_REDUCE_CHUNK", MSM_REDUCE_CHUNK_DEFAULT);
+    const size_t npart = (size_t)nbuckets / (s.reduce_chunk * 32) + 64;
+    if (with_sort) {
+        CUDA_CHECK(cudaMalloc(&s.counts, (size_t)nbuckets * 4));
+        CUDA_CHECK(cudaMalloc(&s.offsets, ((size_t)nbuckets + 1) * 4));
+        CUDA_CHECK(cudaMalloc(&s.cursor, (size_t)nbuckets * 4));
+        CUDA_CHECK(cudaMalloc(&s.entries, (nent + 1) * 4));
+        CUDA_CHECK(cudaMalloc(&s.scalars_canon, ((size_t)n + 1) * sizeof(fe)));
+    }
     CUDA_CHECK(cudaMalloc(&s.big_list, (size_t)nbuckets * 4));
     CUDA_CHECK(cudaMalloc(&s.big_count, 4));
     CUDA_CHECK(cudaMalloc(&s.frag_first, nchunks * pt));
@@ -291,57 +300,82 @@ void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, b
     CUDA_CHECK(cudaMalloc(&s.buckets, (size_t)nbuckets * pt));
     CUDA_CHECK(cudaMalloc(&s.partials, (npart + 1) * pt));
     CUDA_CHECK(cudaMalloc(&s.result, pt)); s.result_owned = true;
-    CUDA_CHECK(cudaMalloc(&s.scalars_canon, ((size_t)n + 1) * sizeof(fe)));
+    if (env_u32("B2G_MSM_TAIL_PRIORITY", 1) == 1) {
+        // the tail kernels occupy a handful of CTAs for a long dependent chain: let them be dispatched ahead of the
+        // thousands of pending accumulation CTAs of the other queries
+        int least = 0, greatest = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&s.tail, cudaStreamNonBlocking, greatest));
+        CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_acc, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_tail, cudaEventDisableTiming));
+    }
 }
 
 void msm_scratch_free(MsmScratch& s) {
     void* ptrs[] = {s.counts, s.offsets, s.cursor, s.entries, s.big_list, s.big_count, s.frag_first, s.frag_last,
                     s.buckets, s.partials, s.result_owned ? s.result : nullptr, s.scalars_canon};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (s.tail) { cudaStreamDestroy(s.tail); cudaEventDestroy(s.ev_acc); cudaEventDestroy(s.ev_tail); }
     s = MsmScratch();
 }
 
-template <class C, class F>
-static void msm_run_t(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st) {
-    using Pt = typename C::Pt;
-    const size_t ptb = sizeof(Pt);
+void msm_sort(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st) {
     if (n > plan.n) n = plan.n;                                  // msm_bigint truncates to the shorter side
-    if (n == 0 || plan.table == nullptr) { CUDA_CHECK(cudaMemsetAsync(s.result, 0, ptb, st)); return; }
-    if (n > s.cap_n || plan.nwin > s.cap_nwin || plan.nbuckets > s.cap_buckets) throw_error(B2G_E_SHAPE, "msm: scratch too small");
-    const uint32_t nb = plan.nbuckets, chunk = s.chunk;
+    s.sorted_n = n;
+    if (n == 0 || plan.table == nullptr) return;
+    if (n > s.cap_n || plan.nwin > s.cap_nwin || plan.nbuckets > s.cap_buckets || !s.entries) throw_error(B2G_E_SHAPE, "msm: sort scratch too small");
+    const uint32_t nb = plan.nbuckets;
     CUDA_CHECK(cudaMemsetAsync(s.counts, 0, (size_t)nb * 4, st));
     msm_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(scalars_dev, n, scalars_mont ? 1 : 0, plan.c, plan.nwin, s.scalars_canon, s.counts);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(s.counts, nb, s.offsets, s.cursor, s.big_count);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(s.counts, nb, s.offsets, s.cursor);
     // table rows are indexed w * plan.n + i (the table was built over plan.n bases, n may be shorter)
     msm_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.scalars_canon, n, plan.n, plan.c, plan.nwin, s.offsets, s.cursor, s.entries);
-    const uint64_t nent = (uint64_t)n * plan.nwin;
-    const uint32_t nthreads = (uint32_t)((nent + chunk - 1) / chunk);
-    if (s.prof0) CUDA_CHECK(cudaEventRecord(s.prof0, st));
-    msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, 0, st>>>(plan.table, s.entries, s.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
-    if (s.prof1) CUDA_CHECK(cudaEventRecord(s.prof1, st));
-    msm_fold_kernel<C, F><<<(nb + 127) / 128, 128, 0, st>>>(s.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
-    const size_t sh = (size_t)MSM_TREE_THREADS * ptb;
-    msm_fold_big_kernel<C, F><<<64, MSM_TREE_THREADS, sh, st>>>(s.offsets, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
-    const uint32_t nred = (nb + MSM_REDUCE_CHUNK - 1) / MSM_REDUCE_CHUNK;
-    const uint32_t npart = (nred + MSM_TREE_THREADS - 1) / MSM_TREE_THREADS;
-    msm_reduce_kernel<C, F><<<npart, MSM_TREE_THREADS, sh, st>>>(s.buckets, nb, s.partials);
-    msm_sum_kernel<C, F><<<1, MSM_TREE_THREADS, sh, st>>>(s.partials, npart, s.result);
-    g_launch_count += 9;
+    g_launch_count += 3;
     CUDA_CHECK(cudaGetLastError());
 }
 
-void msm_run(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st) {
-    if (plan.g2) msm_run_t<G2, Fq2>(plan, s, scalars_dev, n, scalars_mont, st);
-    else msm_run_t<G1, Fq>(plan, s, scalars_dev, n, scalars_mont, st);
+template <class C, class F>
+static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmScratch& s, cudaStream_t st) {
+    using Pt = typename C::Pt;
+    const size_t ptb = sizeof(Pt);
+    const uint32_t n = sorted.sorted_n;
+    if (n == 0 || plan.table == nullptr) { CUDA_CHECK(cudaMemsetAsync(s.result, 0, ptb, st)); return; }
+    if (plan.nbuckets > s.cap_buckets || n > s.cap_n || plan.nwin > s.cap_nwin) throw_error(B2G_E_SHAPE, "msm: accumulate scratch too small");
+    const uint32_t nb = plan.nbuckets, chunk = sorted.chunk;
+    CUDA_CHECK(cudaMemsetAsync(s.big_count, 0, 4, st));
+    const uint64_t nent = (uint64_t)n * plan.nwin;
+    const uint32_t nthreads = (uint32_t)((nent + chunk - 1) / chunk);
+    if (s.prof0) CUDA_CHECK(cudaEventRecord(s.prof0, st));
+    msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
+    if (s.prof1) CUDA_CHECK(cudaEventRecord(s.prof1, st));
+    cudaStream_t main_st = st;
+    if (s.tail) { CUDA_CHECK(cudaEventRecord(s.ev_acc, st)); CUDA_CHECK(cudaStreamWaitEvent(s.tail, s.ev_acc, 0)); st = s.tail; }
+    msm_fold_kernel<C, F><<<(nb + 127) / 128, 128, 0, st>>>(sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
+    constexpr int NT = TailThreads<F>::N;
+    const size_t sh = (size_t)NT * ptb;
+    msm_fold_big_kernel<C, F><<<128, NT, sh, st>>>(sorted.offsets, chunk, s.buckets, s.frag_first, s.frag_last, s.big_list, s.big_count);
+    const uint32_t rchunk = s.reduce_chunk;
+    const uint32_t nred = (nb + rchunk - 1) / rchunk;
+    const uint32_t npart = (nred + NT - 1) / NT;
+    msm_reduce_kernel<C, F><<<npart, NT, sh, st>>>(s.buckets, nb, rchunk, s.partials);
+    msm_sum_kernel<C, F><<<1, NT, sh, st>>>(s.partials, npart, s.result);
+    if (s.tail) { CUDA_CHECK(cudaEventRecord(s.ev_tail, s.tail)); CUDA_CHECK(cudaStreamWaitEvent(main_st, s.ev_tail, 0)); }
+    g_launch_count += 5;
+    CUDA_CHECK(cudaGetLastError());
 }
 
-void msm_init_kernels() {
-    const int shg1 = MSM_TREE_THREADS * (int)sizeof(G1::Pt), shg2 = MSM_TREE_THREADS * (int)sizeof(G2::Pt);
-    (void)shg1;
-    // 128 x 256 B = 32 KiB for G2: below the 48 KiB default, no opt-in needed; keep the attribute call for safety
-    CUDA_CHECK(cudaFuncSetAttribute(msm_fold_big_kernel<G2, Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shg2));
-    CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_kernel<G2, Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shg2));
-    CUDA_CHECK(cudaFuncSetAttribute(msm_sum_kernel<G2, Fq2>, cudaFuncAttributeMaxDynamicSharedMemorySize, shg2));
+// bucket accumulation + reduction of `plan`'s table against an already sorted scalar vector (`sorted` may be shared by
+// several queries that pair the same scalars with different bases: A, B1, B2, L all use the witness)
+void msm_accumulate(const MsmPlan& plan, const MsmScratch& sorted, MsmScratch& acc, cudaStream_t st) {
+    if (plan.g2) msm_accumulate_t<G2, Fq2>(plan, sorted, acc, st);
+    else msm_accumulate_t<G1, Fq>(plan, sorted, acc, st);
 }
+
+void msm_run(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st) {
+    msm_sort(plan, s, scalars_dev, n, scalars_mont, st);
+    msm_accumulate(plan, s, s, st);
+}
+
+void msm_init_kernels() {}   // all tail kernels use < 48 KiB of dynamic shared memory
 
 }  // namespace b2g

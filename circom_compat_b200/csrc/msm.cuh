@@ -19,7 +19,6 @@
 namespace b2g {
 
 constexpr int MSM_MAX_WIN = 32;          // c >= 8
-constexpr int MSM_REDUCE_CHUNK = 16;     // buckets per thread in the weighted reduction
 constexpr int MSM_BIG_FRAGS = 32;        // buckets with more fragments than this are folded by a whole CTA
 
 struct MsmPlan {                         // static per query
@@ -31,20 +30,22 @@ struct MsmPlan {                         // static per query
 };
 
 struct MsmScratch {                      // one per in-flight MSM
-    uint32_t cap_n = 0; int cap_nwin = 0; uint32_t cap_buckets = 0; uint32_t chunk = 64;
+    uint32_t cap_n = 0; int cap_nwin = 0; uint32_t cap_buckets = 0; uint32_t chunk = 64; uint32_t sorted_n = 0; uint32_t reduce_chunk = 8;
     uint32_t *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *entries = nullptr;
     uint32_t *big_list = nullptr, *big_count = nullptr;
     void *frag_first = nullptr, *frag_last = nullptr, *buckets = nullptr, *partials = nullptr, *result = nullptr;
     fe* scalars_canon = nullptr;         // n canonical scalars (filled by the digit pass)
     bool g2 = false, result_owned = false;
     cudaEvent_t prof0 = nullptr, prof1 = nullptr;   // optional: bracket the accumulate kernel (b2g_bench_msm)
+    cudaStream_t tail = nullptr;                     // high-priority stream for the low-parallelism fold / weighted-sum kernels
+    cudaEvent_t ev_acc = nullptr, ev_tail = nullptr;
 };
 
 inline int msm_pick_c(uint32_t n) {
     int lg = 0; while ((1ull << (lg + 1)) <= n) lg++;
     int c = lg - 3;
     if (c < 8) c = 8;
-    if (c > 16) c = 16;
+    if (c > 16) c = 16;                  // B2G_MSM_C overrides (8..22) for tuning
     return c;
 }
 inline int msm_nwin(int c) { return (255 + c - 1) / c; }

@@ -19,7 +19,9 @@ namespace b2g {
 // from msm.cu
 void msm_build_table(MsmPlan& plan, const void* bases_dev, uint32_t n, bool g2, cudaStream_t st);
 void msm_free_table(MsmPlan& plan);
-void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2);
+void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2, bool with_sort);
+void msm_sort(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st);
+void msm_accumulate(const MsmPlan& plan, const MsmScratch& sorted, MsmScratch& acc, cudaStream_t st);
 void msm_scratch_free(MsmScratch& s);
 void msm_run(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st);
 void msm_init_kernels();
@@ -33,8 +35,8 @@ using namespace b2g;
 
 struct b2g_ctx {
     int device = 0, shard_rank = 0, shard_count = 1;
-    cudaStream_t st[NQ] = {};
-    cudaEvent_t ev_w = nullptr, ev_done[NQ] = {}, ev_t[20] = {};
+    cudaStream_t st[NQ] = {}, st_glue = nullptr;
+    cudaEvent_t ev_w = nullptr, ev_sort = nullptr, ev_pre = nullptr, ev_post = nullptr, ev_done[NQ] = {}, ev_t[20] = {};
     MsmScratch scratch[NQ];
     bool scratch_ok = false;
     uint8_t* d_partial = nullptr;        // 768 B: [H, L, A, B1] G1 XYZZ + B2 G2 XYZZ
@@ -47,7 +49,7 @@ struct b2g_ctx {
 };
 
 struct b2g_pk {
-    b2g_ctx* ctx = nullptr;
+    int device = 0, shard_rank = 0, shard_count = 1;   // a key may be used by any ctx of the same device and shard
     uint32_t n_vars = 0, n_public = 0, domain = 0;
     MsmPlan plan[NQ];
     uint32_t lo[NQ] = {}, cnt[NQ] = {}, scalar_off[NQ] = {};
@@ -55,7 +57,7 @@ struct b2g_pk {
 };
 
 struct b2g_mat {
-    b2g_ctx* ctx = nullptr;
+    int device = 0;
     uint32_t m = 0, num_inputs = 0, n_vars = 0, n = 0;
     int logn = 0;
     NttDomain dom;
@@ -263,6 +265,26 @@ static void ensure_witness_buffers(b2g_ctx* ctx, size_t n_vars, size_t n) {
     }
 }
 
+// per-stream MSM scratch of this context, sized for `pk` (re-created if a later key is larger)
+static void ensure_scratch(b2g_ctx* ctx, const b2g_pk* pk) {
+    bool ok = ctx->scratch_ok;
+    for (int q = 0; q < NQ && ok; q++) {
+        const MsmPlan& p = pk->plan[q]; const MsmScratch& sc = ctx->scratch[q];
+        if ((p.n ? p.n : 1) > sc.cap_n || p.nwin > sc.cap_nwin || p.nbuckets > sc.cap_buckets) ok = false;
+    }
+    if (ok) return;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (ctx->scratch_ok) { for (int q = 0; q < NQ; q++) msm_scratch_free(ctx->scratch[q]); ctx->scratch_ok = false; }
+    for (int q = 0; q < NQ; q++) {
+        const MsmPlan& p = pk->plan[q];
+        msm_scratch_alloc(ctx->scratch[q], p.n ? p.n : 1, p.nwin, p.nbuckets, q == Q_B2, q == Q_H || q == Q_L);
+        cudaFree(ctx->scratch[q].result);
+        ctx->scratch[q].result = ctx->d_partial + PARTIAL_OFF[q];
+        ctx->scratch[q].result_owned = false;
+    }
+    ctx->scratch_ok = true;
+}
+
 static void run_witness_map(b2g_ctx* ctx, b2g_mat* mat, cudaStream_t st) {
     spmv_launch(mat->n, mat->m, mat->num_inputs, mat->a_rowptr, mat->a_col, mat->a_val, mat->b_rowptr, mat->b_col, mat->b_val,
                 ctx->d_w, ctx->d_a, ctx->d_b, ctx->d_c, st);
@@ -271,20 +293,27 @@ static void run_witness_map(b2g_ctx* ctx, b2g_mat* mat, cudaStream_t st) {
 
 static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
     if (!ctx || !pk || !mat) throw_error(B2G_E_SHAPE, "null handle");
-    if (pk->ctx != ctx || mat->ctx != ctx) throw_error(B2G_E_SHAPE, "handle belongs to another context");
+    if (pk->device != ctx->device || mat->device != ctx->device) throw_error(B2G_E_SHAPE, "handle belongs to another device");
+    if (pk->shard_rank != ctx->shard_rank || pk->shard_count != ctx->shard_count) throw_error(B2G_E_SHAPE, "proving key was loaded for another shard");
     if (pk->n_vars != mat->n_vars) throw_error(B2G_E_SHAPE, "proving key and matrices disagree on n_vars");
     if (pk->domain != mat->n) throw_error(B2G_E_SHAPE, "proving key domain_size != next_pow2(num_constraints + num_inputs)");
     if (pk->n_public + 1 != mat->num_inputs) throw_error(B2G_E_SHAPE, "proving key n_public + 1 != num_inputs");
 }
 
-// device part of a proof up to the five partial MSM results (witness must already be in ctx->d_w)
+// device part of a proof up to the five partial MSM results (witness must already be in ctx->d_w).
+// The four witness-scalar queries (L, A, B1, B2) are defined over the same index range and share ONE digit sort.
+static const int WITNESS_ORDER[4] = {Q_B2, Q_A, Q_B1, Q_L};     // the G2 MSM is the longest: start it first
+
 static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
-    cudaStream_t s0 = ctx->st[0];
+    cudaStream_t s0 = ctx->st[0], ssort = ctx->st[Q_L];
     CUDA_CHECK(cudaEventRecord(ctx->ev_w, s0));
-    for (int q = 1; q < NQ; q++) {
-        CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_w, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(ssort, ctx->ev_w, 0));
+    msm_sort(pk->plan[Q_A], ctx->scratch[Q_L], ctx->d_w + pk->scalar_off[Q_A] + pk->lo[Q_A], pk->cnt[Q_A], true, ssort);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_sort, ssort));
+    for (int q : WITNESS_ORDER) {
+        if (q != Q_L) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sort, 0));
         if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q], ctx->st[q]));
-        msm_run(pk->plan[q], ctx->scratch[q], ctx->d_w + pk->scalar_off[q] + pk->lo[q], pk->cnt[q], true, ctx->st[q]);
+        msm_accumulate(pk->plan[q], ctx->scratch[Q_L], ctx->scratch[q], ctx->st[q]);
         if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q + 1], ctx->st[q]));
         CUDA_CHECK(cudaEventRecord(ctx->ev_done[q], ctx->st[q]));
     }
@@ -299,11 +328,21 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
 
 static Scalar256 load_scalar(const void* p) { Scalar256 s; memcpy(s.l, p, 32); return s; }
 
-static void launch_glue(b2g_ctx* ctx, b2g_pk* pk, const uint8_t* partials_dev, int count, const void* r, const void* s, cudaStream_t st) {
+// r*delta1, s*delta1, rs*delta1, s*delta2 depend only on (r, s): issued on a side stream before the MSMs
+static void launch_glue_pre(b2g_ctx* ctx, b2g_pk* pk, const void* r, const void* s) {
     Scalar256 rr = load_scalar(r), ss = load_scalar(s);
-    glue_pre_kernel<<<1, 128, 0, st>>>(pk->d_consts, rr, ss, ctx->d_pre);
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_post, 0));      // d_pre of the previous proof is no longer read
+    glue_pre_kernel<<<1, 128, 0, ctx->st_glue>>>(pk->d_consts, rr, ss, ctx->d_pre);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_pre, ctx->st_glue));
+    g_launch_count += 1;
+}
+
+static void launch_glue_post(b2g_ctx* ctx, b2g_pk* pk, const uint8_t* partials_dev, int count, const void* r, const void* s, cudaStream_t st) {
+    Scalar256 rr = load_scalar(r), ss = load_scalar(s);
+    CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pre, 0));
     glue_post_kernel<<<1, 128, 0, st>>>(partials_dev, count, pk->d_consts, ctx->d_pre, rr, ss, ctx->d_proof);
-    g_launch_count += 2;
+    CUDA_CHECK(cudaEventRecord(ctx->ev_post, st));
+    g_launch_count += 1;
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -341,6 +380,10 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         ctx->device = device; ctx->shard_rank = shard_rank; ctx->shard_count = shard_count;
         for (int i = 0; i < NQ; i++) { CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st[i], cudaStreamNonBlocking)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_w, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sort, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_post, cudaEventDisableTiming));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st_glue, cudaStreamNonBlocking));
         for (auto& e : ctx->ev_t) CUDA_CHECK(cudaEventCreate(&e));
         CUDA_CHECK(cudaMalloc(&ctx->d_partial, B2G_PARTIAL_BYTES));
         CUDA_CHECK(cudaMalloc(&ctx->d_partials_all, 64 * B2G_PARTIAL_BYTES));
@@ -357,7 +400,7 @@ int b2g_ctx_destroy(b2g_ctx* ctx) {
         DevGuard g(ctx->device);
         cudaDeviceSynchronize();
         for (int i = 0; i < NQ; i++) { if (ctx->scratch_ok) msm_scratch_free(ctx->scratch[i]); cudaStreamDestroy(ctx->st[i]); cudaEventDestroy(ctx->ev_done[i]); }
-        cudaEventDestroy(ctx->ev_w);
+        cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_post); cudaStreamDestroy(ctx->st_glue);
         for (auto& e : ctx->ev_t) cudaEventDestroy(e);
         for (void* p : {(void*)ctx->d_partial, (void*)ctx->d_partials_all, (void*)ctx->d_proof, (void*)ctx->d_pre, (void*)ctx->d_w,
                         (void*)ctx->d_a, (void*)ctx->d_b, (void*)ctx->d_c, (void*)ctx->d_h}) if (p) cudaFree(p);
@@ -374,13 +417,18 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
         DevGuard g(ctx->device);
         cudaStream_t st = ctx->st[0];
         b2g_pk* pk = new b2g_pk();
-        pk->ctx = ctx; pk->n_vars = d->n_vars; pk->n_public = d->n_public; pk->domain = d->domain_size;
+        pk->device = ctx->device; pk->shard_rank = ctx->shard_rank; pk->shard_count = ctx->shard_count; pk->n_vars = d->n_vars; pk->n_public = d->n_public; pk->domain = d->domain_size;
         const uint32_t li = d->n_public + 1;
         // query sizes as paired with scalars by create_proof_with_assignment
-        const uint32_t total[NQ] = {d->domain_size, d->n_vars - li, d->n_vars - 1, d->n_vars - 1, d->n_vars - 1};
+        // L, A, B1, B2 all pair bases with w[1..n_vars): L is re-indexed onto that range by prepending (l - 1) points at
+        // infinity (l_query[j] belongs to w[l + j]), so the four queries share one digit sort per proof.
+        if (d->n_vars - li && !d->l_query) throw_error(B2G_E_SHAPE, "null proving-key section");
+        std::vector<uint8_t> l_padded((size_t)(d->n_vars - 1) * 64, 0);
+        if (d->n_vars - li) memcpy(l_padded.data() + (size_t)(li - 1) * 64, d->l_query, (size_t)(d->n_vars - li) * 64);
+        const uint32_t total[NQ] = {d->domain_size, d->n_vars - 1, d->n_vars - 1, d->n_vars - 1, d->n_vars - 1};
         const uint32_t base_skip[NQ] = {0, 0, 1, 1, 1};             // query[0] is added separately for A/B1/B2
-        const uint32_t soff[NQ] = {0, li, 1, 1, 1};                 // first scalar: h[0] / w[l] / w[1]
-        const void* src[NQ] = {d->h_query, d->l_query, d->a_query, d->b_g1_query, d->b_g2_query};
+        const uint32_t soff[NQ] = {0, 1, 1, 1, 1};                  // first scalar: h[0] / w[1]
+        const void* src[NQ] = {d->h_query, l_padded.data(), d->a_query, d->b_g1_query, d->b_g2_query};
         for (int q = 0; q < NQ; q++) {
             const bool g2 = q == Q_B2;
             const size_t aff = g2 ? 128 : 64;
@@ -402,16 +450,6 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
         memcpy(&consts[320], d->beta_g2, 128); memcpy(&consts[448], d->delta_g2, 128); memcpy(&consts[576], d->b_g2_query, 128);
         pk->d_consts = dev_upload<uint8_t>(consts.data(), consts.size(), st);
         CUDA_CHECK(cudaStreamSynchronize(st));
-        // per-stream MSM scratch sized for this key (re-created if a later key is larger)
-        if (ctx->scratch_ok) { for (int q = 0; q < NQ; q++) msm_scratch_free(ctx->scratch[q]); ctx->scratch_ok = false; }
-        for (int q = 0; q < NQ; q++) {
-            const MsmPlan& p = pk->plan[q];
-            msm_scratch_alloc(ctx->scratch[q], p.n ? p.n : 1, p.nwin, p.nbuckets, q == Q_B2);
-            cudaFree(ctx->scratch[q].result);
-            ctx->scratch[q].result = ctx->d_partial + PARTIAL_OFF[q];
-            ctx->scratch[q].result_owned = false;
-        }
-        ctx->scratch_ok = true;
         *out = pk;
     });
 }
@@ -419,7 +457,7 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
 int b2g_pk_free(b2g_pk* pk) {
     return guarded([&] {
         if (!pk) return;
-        DevGuard g(pk->ctx->device);
+        DevGuard g(pk->device);
         cudaDeviceSynchronize();
         for (int q = 0; q < NQ; q++) msm_free_table(pk->plan[q]);
         if (pk->d_consts) cudaFree(pk->d_consts);
@@ -444,7 +482,7 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
         DevGuard g(ctx->device);
         cudaStream_t st = ctx->st[0];
         b2g_mat* mat = new b2g_mat();
-        mat->ctx = ctx; mat->m = m; mat->num_inputs = d->num_inputs; mat->n_vars = d->n_vars; mat->logn = logn; mat->n = 1u << logn;
+        mat->device = ctx->device; mat->m = m; mat->num_inputs = d->num_inputs; mat->n_vars = d->n_vars; mat->logn = logn; mat->n = 1u << logn;
         mat->a_rowptr = dev_upload<uint32_t>(d->a_rowptr, ((size_t)m + 1) * 4, st);
         mat->b_rowptr = dev_upload<uint32_t>(d->b_rowptr, ((size_t)m + 1) * 4, st);
         mat->a_col = dev_upload<uint32_t>(d->a_col, (size_t)annz * 4, st);
@@ -461,7 +499,7 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
 int b2g_matrices_free(b2g_mat* mat) {
     return guarded([&] {
         if (!mat) return;
-        DevGuard g(mat->ctx->device);
+        DevGuard g(mat->device);
         cudaDeviceSynchronize();
         ntt_domain_destroy(mat->dom);
         for (void* p : {(void*)mat->a_rowptr, (void*)mat->a_col, (void*)mat->b_rowptr, (void*)mat->b_col, (void*)mat->a_val, (void*)mat->b_val}) if (p) cudaFree(p);
@@ -472,7 +510,7 @@ int b2g_matrices_free(b2g_mat* mat) {
 int b2g_witness_map(b2g_ctx* ctx, b2g_mat* mat, const void* w_mont, void* h_out, uint32_t* domain_size_out) {
     return guarded([&] {
         if (!ctx || !mat || !w_mont) throw_error(B2G_E_SHAPE, "null pointer");
-        if (mat->ctx != ctx) throw_error(B2G_E_SHAPE, "handle belongs to another context");
+        if (mat->device != ctx->device) throw_error(B2G_E_SHAPE, "handle belongs to another device");
         DevGuard g(ctx->device);
         cudaStream_t st = ctx->st[0];
         ensure_witness_buffers(ctx, mat->n_vars, mat->n);
@@ -488,6 +526,7 @@ static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_m
     check_shapes(ctx, pk, mat);
     if (!w_mont) throw_error(B2G_E_SHAPE, "null witness");
     ensure_witness_buffers(ctx, mat->n_vars, mat->n);
+    ensure_scratch(ctx, pk);
     cudaStream_t s0 = ctx->st[0];
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[12], s0));
     CUDA_CHECK(cudaMemcpyAsync(ctx->d_w, w_mont, (size_t)mat->n_vars * 32, cudaMemcpyHostToDevice, s0));
@@ -500,10 +539,12 @@ int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const
         if (!ctx || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
         if (ctx->shard_count != 1) throw_error(B2G_E_SHAPE, "b2g_prove needs an unsharded context; use b2g_prove_partial/finish");
         DevGuard g(ctx->device);
+        if (!pk) throw_error(B2G_E_SHAPE, "null handle");
+        launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
         cudaStream_t s0 = ctx->st[0];
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
-        launch_glue(ctx, pk, ctx->d_partial, 1, r_canon, s_canon, s0);
+        launch_glue_post(ctx, pk, ctx->d_partial, 1, r_canon, s_canon, s0);
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
@@ -531,8 +572,9 @@ int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int cou
         if (count < 1 || count > 64) throw_error(B2G_E_SHAPE, "partial count out of range");
         DevGuard g(ctx->device);
         cudaStream_t s0 = ctx->st[0];
+        launch_glue_pre(ctx, pk, r_canon, s_canon);
         CUDA_CHECK(cudaMemcpyAsync(ctx->d_partials_all, partials_all, (size_t)count * B2G_PARTIAL_BYTES, cudaMemcpyHostToDevice, s0));
-        launch_glue(ctx, pk, ctx->d_partials_all, count, r_canon, s_canon, s0);
+        launch_glue_post(ctx, pk, ctx->d_partials_all, count, r_canon, s_canon, s0);
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
     });
@@ -544,12 +586,17 @@ int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* a
         check_shapes(ctx, pk, mat);
         if (ctx->cap_w < mat->n_vars) throw_error(B2G_E_SHAPE, "no witness resident: call b2g_prove first");
         DevGuard g(ctx->device);
+        ensure_scratch(ctx, pk);
         cudaStream_t s0 = ctx->st[0];
-        Scalar256 one = {{1, 0, 0, 0, 0, 0, 0, 0}};
+        // representative full-size scalars (the glue cost depends on their bit length)
+        Scalar256 kr = {{0x90abcdefu, 0x12345678u, 0x90abcdefu, 0x12345678u, 0x0badc0deu, 0x0defaced, 0x13572468u, 0x1fedcba9u}};
+        Scalar256 ks = {{0x87654321u, 0xfedcba09u, 0x87654321u, 0xfedcba09u, 0x600dcafeu, 0x0ddba11u, 0x24681357u, 0x2abcdef0u}};
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[16], s0));
         for (int it = 0; it < iters; it++) {
+            CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_t[16], 0));
+            launch_glue_pre(ctx, pk, kr.l, ks.l);
             launch_msms(ctx, pk, mat, false);
-            launch_glue(ctx, pk, ctx->d_partial, 1, one.l, one.l, s0);
+            launch_glue_post(ctx, pk, ctx->d_partial, 1, kr.l, ks.l, s0);
         }
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[17], s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
@@ -566,13 +613,15 @@ int b2g_bench_msm(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int query, int iters, 
         DevGuard g(ctx->device);
         cudaStream_t s0 = ctx->st[0];
         MsmScratch& sc = ctx->scratch[query];
+        MsmScratch& sorter = ctx->scratch[query == Q_H ? Q_H : Q_L];
         const fe* scalars = (query == Q_H ? ctx->d_h : ctx->d_w + pk->scalar_off[query]) + pk->lo[query];
         std::vector<cudaEvent_t> ev(2 * (size_t)iters);
         for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[18], s0));
         for (int it = 0; it < iters; it++) {
             sc.prof0 = ev[2 * it]; sc.prof1 = ev[2 * it + 1];
-            msm_run(pk->plan[query], sc, scalars, pk->cnt[query], true, s0);
+            msm_sort(pk->plan[query], sorter, scalars, pk->cnt[query], true, s0);
+            msm_accumulate(pk->plan[query], sorter, sc, s0);
         }
         sc.prof0 = sc.prof1 = nullptr;
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[19], s0));
@@ -607,7 +656,7 @@ static void msm_entry(b2g_ctx* ctx, const void* bases, const void* scalars, size
     fe* d_sc = dev_upload<fe>(scalars, n * 32, st);
     MsmPlan plan; MsmScratch sc;
     msm_build_table(plan, d_bases, (uint32_t)n, IS_G2, st);
-    msm_scratch_alloc(sc, (uint32_t)n, plan.nwin, plan.nbuckets, IS_G2);
+    msm_scratch_alloc(sc, (uint32_t)n, plan.nwin, plan.nbuckets, IS_G2, true);
     msm_run(plan, sc, d_sc, (uint32_t)n, scalars_mont != 0, st);
     uint8_t* d_out = nullptr; CUDA_CHECK(cudaMalloc(&d_out, aff));
     if (IS_G2) xyzz_to_affine_kernel<G2, Fq2><<<1, 1, 0, st>>>(sc.result, 1, d_out);

@@ -28,22 +28,34 @@ def _c(a, dtype=np.uint64):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+# Device-resident keys / matrices are cached per (host object, device, shard): every Context of that device and shard
+# can use them, so several proofs can be in flight on one GPU (one Context per in-flight proof) without duplicating
+# the 6 GiB of tables.  release(obj) / release_all() free them.
+_PK_HANDLES, _MAT_HANDLES = {}, {}
+
+
+def release(obj):
+    for cache, free in ((_PK_HANDLES, 'b2g_pk_free'), (_MAT_HANDLES, 'b2g_matrices_free')):
+        for key in [k for k in cache if k[0] == id(obj)]:
+            getattr(N.lib(), free)(cache.pop(key)[0])
+
+
+def release_all():
+    for cache, free in ((_PK_HANDLES, 'b2g_pk_free'), (_MAT_HANDLES, 'b2g_matrices_free')):
+        for key in list(cache):
+            getattr(N.lib(), free)(cache.pop(key)[0])
+
+
 class Context:
-    """One b2g_ctx = one GPU (optionally one shard of a base-range-sharded prover)."""
+    """One b2g_ctx = one in-flight proof on one GPU (optionally one shard of a base-range-sharded prover)."""
 
     def __init__(self, device: int = 0, shard_rank: int = 0, shard_count: int = 1):
         self._h = C.c_void_p()
         N.check(N.lib().b2g_ctx_create(device, shard_rank, shard_count, C.byref(self._h)))
         self.device, self.shard_rank, self.shard_count = device, shard_rank, shard_count
-        self._pks, self._mats = {}, {}
 
     def close(self):
         if self._h:
-            for h in self._pks.values():
-                N.lib().b2g_pk_free(h[0])
-            for h in self._mats.values():
-                N.lib().b2g_matrices_free(h[0])
-            self._pks.clear(); self._mats.clear()
             N.lib().b2g_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -53,10 +65,9 @@ class Context:
         except Exception:
             pass
 
-    # device-resident handles are cached per (ctx, host object)
     def pk_handle(self, pk: ProvingKey):
-        key = id(pk)
-        if key not in self._pks:
+        key = (id(pk), self.device, self.shard_rank, self.shard_count)
+        if key not in _PK_HANDLES:
             d = N.PkDesc()
             d.n_vars, d.n_public, d.domain_size = pk.n_vars, pk.n_public, pk.domain_size
             keep = {}
@@ -65,12 +76,12 @@ class Context:
                 setattr(d, name, keep[name].ctypes.data if keep[name].size else None)
             h = C.c_void_p()
             N.check(N.lib().b2g_pk_load(self._h, C.byref(d), C.byref(h)))
-            self._pks[key] = (h, pk)
-        return self._pks[key][0]
+            _PK_HANDLES[key] = (h, pk)
+        return _PK_HANDLES[key][0]
 
     def mat_handle(self, m: ConstraintMatrices, n_vars: int):
-        key = id(m)
-        if key not in self._mats:
+        key = (id(m), self.device, n_vars)
+        if key not in _MAT_HANDLES:
             d = N.MatDesc()
             d.num_constraints, d.num_inputs, d.n_vars = m.num_constraints, m.num_instance_variables, n_vars
             keep = [_c(m.a[0], np.uint32), _c(m.a[1], np.uint32), _c(m.a[2]), _c(m.b[0], np.uint32), _c(m.b[1], np.uint32), _c(m.b[2])]
@@ -78,8 +89,8 @@ class Context:
                 setattr(d, name, arr.ctypes.data if arr.size else None)
             h = C.c_void_p()
             N.check(N.lib().b2g_matrices_load(self._h, C.byref(d), C.byref(h)))
-            self._mats[key] = (h, m)
-        return self._mats[key][0]
+            _MAT_HANDLES[key] = (h, m)
+        return _MAT_HANDLES[key][0]
 
     def last_timings(self) -> dict:
         buf = (C.c_float * 16)()

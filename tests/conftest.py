@@ -33,6 +33,8 @@ def complex_zkey_bytes():
 def ctx():
     """A real device context.  GPU tests never skip and never fall back: no CUDA => failure."""
     from circom_compat_b200 import Context
+    from circom_compat_b200 import release_all
     c = Context(0)
     yield c
+    release_all()
     c.close()
