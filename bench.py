@@ -161,7 +161,7 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from circom_compat_b200 import Context, Groth16, fr_to_mont, synth
+    from circom_compat_b200 import Context, Groth16, fr_to_mont, synth, sharding
 
     sharded = world > 1 and args.mode == 'sharded'
     inflight = 1 if sharded else max(1, args.inflight)
@@ -180,15 +180,10 @@ def run_ours(args):
     wm = wms[0]
     n_vars = circ.n_vars
 
-    gather_buf = torch.empty((world, 768), dtype=torch.uint8, device=f'cuda:{local}') if sharded else None
-
     def one_proof(i=0):
         if not sharded:
             return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wms[i], ctxs[i])
-        part = Groth16.prove_partial(pk, cm, wm, ctx)
-        mine = torch.from_numpy(part).to(f'cuda:{local}', non_blocking=True)
-        dist.all_gather_into_tensor(gather_buf.view(-1), mine)
-        return Groth16.prove_finish(pk, gather_buf.cpu().numpy(), R_FIX, S_FIX, ctx)
+        return sharding.prove_sharded(ctx, pk, cm, wm, R_FIX, S_FIX, dist, f'cuda:{local}')
 
     t0 = time.time()
     proof = one_proof()          # also loads the key (tables) onto the device

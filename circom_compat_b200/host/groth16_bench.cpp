@@ -1,0 +1,92 @@
+// groth16_bench.cpp - C++ counterpart of /root/reference/benches/groth16.rs:13-85: read a zkey, obtain the full assignment,
+// draw / take (r, s), call Groth16::create_proof_with_reduction_and_matrices repeatedly and report the time per proof.
+//
+//   groth16_bench --parse-only <circuit.zkey>                      host-only: print what read_zkey produced (no GPU)
+//   groth16_bench <circuit.zkey> chain:<a>|<witness.wtns> [iters] [r_hex s_hex]
+//       chain:<a> = the witness of the reference's squaring-chain bench family for input a
+//       (test-vectors/complex-circuit/input.json has a = 3), computed on the host instead of by WASM.
+#include <chrono>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include "ark_circom_b200.hpp"
+
+using namespace ark_circom;
+
+static uint64_t fnv(const void* p, size_t n, uint64_t h = 1469598103934665603ULL) {
+    const uint8_t* b = (const uint8_t*)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+static BigInt256 parse_hex(const std::string& s) {
+    BigInt256 b = {{0, 0, 0, 0}};
+    std::string t = s.rfind("0x", 0) == 0 ? s.substr(2) : s;
+    if (t.size() > 64) throw std::invalid_argument("scalar too long");
+    for (char c : t) {
+        int v = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : (c >= 'A' && c <= 'F') ? c - 'A' + 10 : -1;
+        if (v < 0) throw std::invalid_argument("bad hex digit");
+        for (int i = 3; i > 0; i--) b.l[i] = (b.l[i] << 4) | (b.l[i - 1] >> 60);
+        b.l[0] = (b.l[0] << 4) | (uint64_t)v;
+    }
+    return b;
+}
+
+// witness of the squaring chain [1, c, a, a^2, a^4, ...] (App. B.4 of SURVEY.md), Montgomery form
+static std::vector<Fr> chain_witness(size_t n_vars, uint64_t a) {
+    std::vector<Fr> w(n_vars);
+    w[0] = Fr::from_u64(1);
+    if (n_vars > 2) w[2] = Fr::from_u64(a);
+    for (size_t k = 3; k < n_vars; k++) detail::fr_mont_mul(w[k].l, w[k - 1].l, w[k - 1].l);
+    if (n_vars > 2) detail::fr_mont_mul(w[1].l, w[n_vars - 1].l, w[n_vars - 1].l);
+    return w;
+}
+
+int main(int argc, char** argv) {
+    try {
+        if (argc >= 3 && std::string(argv[1]) == "--parse-only") {
+            std::ifstream f(argv[2], std::ios::binary);
+            if (!f) throw SerializationError("cannot open zkey");
+            auto kv = read_zkey(f);
+            const ProvingKey& pk = kv.first; const ConstraintMatrices& m = kv.second;
+            std::printf("n_vars=%zu n_public=%zu domain=%zu num_constraints=%zu num_instance=%zu num_witness=%zu a_nnz=%zu b_nnz=%zu\n",
+                        pk.a_query.size(), pk.vk.gamma_abc_g1.size() - 1, pk.h_query.size(), m.num_constraints, m.num_instance_variables,
+                        m.num_witness_variables, m.a_num_non_zero, m.b_num_non_zero);
+            std::printf("fnv a=%016llx b1=%016llx b2=%016llx l=%016llx h=%016llx alpha=%016llx\n",
+                        (unsigned long long)fnv(pk.a_query.data(), pk.a_query.size() * 64), (unsigned long long)fnv(pk.b_g1_query.data(), pk.b_g1_query.size() * 64),
+                        (unsigned long long)fnv(pk.b_g2_query.data(), pk.b_g2_query.size() * 128), (unsigned long long)fnv(pk.l_query.data(), pk.l_query.size() * 64),
+                        (unsigned long long)fnv(pk.h_query.data(), pk.h_query.size() * 64), (unsigned long long)fnv(&pk.vk.alpha_g1, 64));
+            uint64_t hc = 1469598103934665603ULL;
+            for (const Matrix* mm : {&m.a, &m.b})
+                for (const auto& row : *mm) for (const auto& e : row) { hc = fnv(e.first.l, 32, hc); uint32_t c = (uint32_t)e.second; hc = fnv(&c, 4, hc); }
+            std::printf("fnv coefs=%016llx\n", (unsigned long long)hc);
+            return 0;
+        }
+        if (argc < 3) { std::fprintf(stderr, "usage: %s [--parse-only] <zkey> chain:<a>|<wtns> [iters] [r_hex s_hex]\n", argv[0]); return 2; }
+        std::ifstream f(argv[1], std::ios::binary);
+        if (!f) throw SerializationError("cannot open zkey");
+        auto kv = read_zkey(f);                                     // benches/groth16.rs:20-23
+        const ProvingKey& params = kv.first; const ConstraintMatrices& matrices = kv.second;
+        const size_t num_inputs = matrices.num_instance_variables, num_constraints = matrices.num_constraints;
+        std::string wsrc = argv[2];
+        std::vector<Fr> full_assignment;
+        if (wsrc.rfind("chain:", 0) == 0) full_assignment = chain_witness(params.a_query.size(), std::stoull(wsrc.substr(6)));
+        else { std::ifstream wf(wsrc, std::ios::binary); if (!wf) throw SerializationError("cannot open wtns"); full_assignment = read_wtns(wf); }
+        int iters = argc > 3 ? std::atoi(argv[3]) : 10;
+        Fr r, s;
+        if (argc > 5) { r = Fr::from_bigint(parse_hex(argv[4])); s = Fr::from_bigint(parse_hex(argv[5])); }
+        else { std::mt19937_64 rng(0xB200); r = Fr::rand(rng); s = Fr::rand(rng); }      // benches/groth16.rs:45-50
+        Proof proof = Groth16::create_proof_with_reduction_and_matrices(params, r, s, matrices, num_inputs, num_constraints, full_assignment);
+        std::printf("proof=%s\n", proof.hex().c_str());
+        auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < iters; i++)                             // benches/groth16.rs:69-84
+            proof = Groth16::create_proof_with_reduction_and_matrices(params, r, s, matrices, num_inputs, num_constraints, full_assignment);
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (iters > 0 ? iters : 1);
+        std::printf("groth proof %zu constraints: %.3f ms/proof over %d iterations\n", num_constraints, ms, iters);
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+}

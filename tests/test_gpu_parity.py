@@ -248,3 +248,24 @@ def test_error_behaviour(ctx, test_zkey_bytes):
         Groth16.create_proof_with_reduction_and_matrices(pk, 1, 1, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont([1, 2, 3]), ctx)
     with pytest.raises(B2gError):
         ctx.ntt(np.zeros((1 << 3, 4), dtype=np.uint64)[:0].reshape(0, 4)) if False else ctx.test_op(99, np.zeros((1, 4), dtype=np.uint64))
+
+
+def test_cpp_host_mirror_proves_golden(golden, tmp_path):
+    """C++ host layer (read_zkey -> Groth16::create_proof_with_reduction_and_matrices, the shape of benches/groth16.rs)
+    reproduces the golden proof bytes; .wtns input and the host-computed chain witness."""
+    import struct, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, 'circom_compat_b200', 'host', 'groth16_bench')
+    g = golden['complex_zkey']
+    out = subprocess.check_output([exe, os.path.join(root, 'tests', 'golden', 'complex-circuit-10000-10000.zkey'), 'chain:%d' % g['a'], '2',
+                                   '%x' % int(g['r']), '%x' % int(g['s'])], text=True)
+    assert 'proof=' + g['proof_hex'] in out
+    gt = golden['test_zkey']
+    w = [int(x) for x in gt['witness']]
+    wt = tmp_path / 'w.wtns'
+    sec1 = struct.pack('<I', 32) + o.R_MOD.to_bytes(32, 'little') + struct.pack('<I', len(w))
+    sec2 = b''.join(x.to_bytes(32, 'little') for x in w)
+    wt.write_bytes(b'wtns' + struct.pack('<II', 2, 2) + struct.pack('<IQ', 1, len(sec1)) + sec1 + struct.pack('<IQ', 2, len(sec2)) + sec2)
+    case = gt['proofs'][0]
+    out = subprocess.check_output([exe, os.path.join(root, 'tests', 'golden', 'test.zkey'), str(wt), '1', '%x' % int(case['r']), '%x' % int(case['s'])], text=True)
+    assert 'proof=' + case['proof_hex'] in out

@@ -99,3 +99,36 @@ def test_synthetic_setup_is_a_valid_groth16_key(kind, tmp_path):
     assert o.G1.mul(o.G1_GEN, da) == proof[0] and o.G2.mul(o.G2_GEN, db) == proof[1] and o.G1.mul(o.G1_GEN, dc) == proof[2]
     pk2, cm2 = read_zkey(data)
     assert pk2.n_vars == circ.n_vars and cm2.num_constraints == circ.num_constraints
+
+
+# ------------------------------------------------------------------------------------------------ C++ host mirror
+HOST_BIN = os.path.join(ROOT, 'circom_compat_b200', 'host', 'groth16_bench')
+
+
+def _fnv(data: bytes, h: int = 1469598103934665603) -> int:
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize('name', ['test.zkey', 'complex-circuit-10000-10000.zkey'])
+def test_cpp_read_zkey_matches_python_reader(name):
+    """ark_circom::read_zkey (circom_compat_b200/host/ark_circom_b200.hpp) vs the Python reader and the oracle's."""
+    import subprocess
+    from circom_compat_b200 import read_zkey
+    path = os.path.join(ROOT, 'tests', 'golden', name)
+    out = subprocess.check_output([HOST_BIN, '--parse-only', path], text=True)
+    kv = dict(re.findall(r'(\w+)=(\w+)', out))
+    pk, cm = read_zkey(path)
+    assert (int(kv['n_vars']), int(kv['n_public']), int(kv['domain'])) == (pk.n_vars, pk.n_public, pk.domain_size)
+    assert (int(kv['num_constraints']), int(kv['num_instance']), int(kv['num_witness'])) == (cm.num_constraints, cm.num_instance_variables, cm.num_witness_variables)
+    assert (int(kv['a_nnz']), int(kv['b_nnz'])) == (cm.a_num_non_zero, cm.b_num_non_zero)
+    for key, arr in (('a', pk.a_query), ('b1', pk.b_g1_query), ('b2', pk.b_g2_query), ('l', pk.l_query), ('h', pk.h_query), ('alpha', pk.alpha_g1)):
+        if arr.size * 8 < 2_000_000:
+            assert int(kv[key], 16) == _fnv(np.ascontiguousarray(arr).tobytes()), key
+    if cm.a_num_non_zero < 1000:
+        h = 1469598103934665603
+        for rowptr, col, val in (cm.a, cm.b):
+            for k in range(len(col)):
+                h = _fnv(val[k].tobytes(), h); h = _fnv(int(col[k]).to_bytes(4, 'little'), h)
+        assert int(kv['coefs'], 16) == h
