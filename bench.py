@@ -160,16 +160,16 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    from circom_compat_b200 import Context, Groth16, fr_to_mont, synth, sharding
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=120))
+    from circom_compat_b200 import Context, Groth16, CircomReduction, fr_to_mont, fr_from_mont, synth, sharding, release_all
+    dev = f'cuda:{local}'
+    inflight = max(1, args.inflight)
 
-    sharded = world > 1 and args.mode == 'sharded'
-    inflight = 1 if sharded else max(1, args.inflight)
-    ctxs = [Context(local, rank if sharded else 0, world if sharded else 1) for _ in range(inflight)]
-    ctx = ctxs[0]
     circ, w = build_workload(args.log_n, args.workload)
+    setup_ctx = Context(local)
     t0 = time.time()
-    pk, td = synth.setup(ctx, circ)
+    pk, td = synth.setup(setup_ctx, circ)
     cm = circ.matrices()
     log(f"[bench] rank {rank}: trapdoor setup + GPU fixed-base key generation {time.time() - t0:.1f}s")
     wm_np = fr_to_mont(w)
@@ -177,34 +177,7 @@ def run_ours(args):
     wms = [p_.numpy().view(np.uint64) for p_ in pinned]
     for w_ in wms:
         w_[...] = wm_np
-    wm = wms[0]
     n_vars = circ.n_vars
-
-    def one_proof(i=0):
-        if not sharded:
-            return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wms[i], ctxs[i])
-        return sharding.prove_sharded(ctx, pk, cm, wm, R_FIX, S_FIX, dist, f'cuda:{local}')
-
-    t0 = time.time()
-    proof = one_proof()          # also loads the key (tables) onto the device
-    log(f"[bench] rank {rank}: key load + first proof {time.time() - t0:.1f}s")
-    # correctness gate: closed-form discrete logs of the unique proof under the trapdoor
-    from circom_compat_b200 import CircomReduction, fr_from_mont
-    if rank == 0 and not args.skip_check:
-        cchk = ctx if not sharded else Context(local)
-        h = fr_from_mont(CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wm, cchk))
-        da, db, dc = synth.expected_proof_dlogs(td, w, h, R_FIX, S_FIX, circ.num_inputs)
-        ea = cchk.fixed_base_g1(synth._ints_to_limbs([da, dc])); eb = cchk.fixed_base_g2(synth._ints_to_limbs([db]))
-        rinv = pow(1 << 256, -1, synth.R_MOD)  # noqa: F841
-        from circom_compat_b200.zkey import Q_MOD
-        qinv = pow(1 << 256, -1, Q_MOD)
-        def canon(a): return [int.from_bytes(np.ascontiguousarray(a).tobytes()[i:i + 32], 'little') * qinv % Q_MOD for i in range(0, a.size * 8, 32)]
-        exp = canon(ea[0]) + canon(eb[0]) + canon(ea[1])
-        got = [int.from_bytes(proof.data[i:i + 32], 'little') for i in range(0, 256, 32)]
-        assert exp == got, "proof does not match the trapdoor's closed-form expectation"
-        log("[bench] proof matches the trapdoor closed form")
-        if sharded:
-            cchk.close()
 
     def barrier():
         torch.cuda.synchronize()
@@ -212,79 +185,128 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(total):
-        """`total` proofs through the public API, `inflight` of them in flight (one host thread + Context each)"""
-        if inflight == 1:
-            out = None
-            for _ in range(total):
-                out = one_proof()
-            return out
-        res = [None] * inflight
-        def worker(i):
-            for _ in range(total // inflight + (1 if i < total % inflight else 0)):
-                res[i] = one_proof(i)
-        ths = [threading.Thread(target=worker, args=(i,)) for i in range(inflight)]
-        [t_.start() for t_ in ths]; [t_.join() for t_ in ths]
-        return res[0]
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-    for i in range(1, inflight):
-        assert one_proof(i).data == proof.data
-    run_steps(max(args.warmup, inflight))
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count()
-    # ---- e2e: host witness in, proof bytes out, every step
-    t0 = time.perf_counter()
-    proof = run_steps(args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    launches = ctx.launch_count() - launches0
-    timings = ctx.last_timings()
-    # ---- device-resident: witness already in HBM (CUDA events inside the library), same number in flight
-    dev_ms = None
-    if not sharded:
-        barrier()
-        per = [args.steps // inflight + (1 if i < args.steps % inflight else 0) for i in range(inflight)]
-        tot = [0.0] * inflight
-        def dev_worker(i):
-            if per[i]:
-                tot[i] = ctxs[i].bench_device(pk, cm, per[i]) * per[i]
-        ths = [threading.Thread(target=dev_worker, args=(i,)) for i in range(inflight)]
+    def threads(fn, n):
+        ths = [threading.Thread(target=fn, args=(i,)) for i in range(n)]
         [t_.start() for t_ in ths]; [t_.join() for t_ in ths]
-        dev_ms = max(tot) / args.steps                      # ms per proof at `inflight` proofs in flight
-        barrier()
-        lat = ctx.bench_device(pk, cm, 5)                   # single proof in flight: latency
-        barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    # max over ranks
-    t = torch.tensor([e2e_s, dev_ms if dev_ms is not None else 0.0], dtype=torch.float64, device=f'cuda:{local}')
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s, dev_ms_max = float(t[0]), float(t[1])
-    proofs_per_step = world if (world > 1 and not sharded) else 1       # replicas: every rank proves its own copy
-    e2e_val = proofs_per_step * args.steps / e2e_s
-    value = proofs_per_step * 1e3 / dev_ms_max if dev_ms is not None else e2e_val
 
-    roof = None
-    extra = {}
+    def measure(mode):
+        """mode: 'single' / 'replicas' (whole proofs per GPU) or 'sharded' (MSM base ranges over the GPUs, NCCL all-gather)."""
+        sharded = mode == 'sharded'
+        # sharded proofs are issued one at a time: two host threads issuing collectives of two communicators onto the
+        # same CUDA stream in rank-dependent order can deadlock (seen with 2 in flight); latency is what sharding buys
+        inflight = 1 if sharded else max(1, args.inflight)
+        ctxs = [Context(local, rank if sharded else 0, world if sharded else 1) for _ in range(inflight)]
+        groups = [None] * inflight
+
+        def one_proof(i=0):
+            if not sharded:
+                return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wms[i], ctxs[i])
+            return sharding.prove_sharded(ctxs[i], pk, cm, wms[i], R_FIX, S_FIX, dist, dev, groups[i])
+
+        def run_steps(total):
+            res = [None] * inflight
+            def worker(i):
+                for _ in range(total // inflight + (1 if i < total % inflight else 0)):
+                    res[i] = one_proof(i)
+            threads(worker, inflight)
+            return res[0]
+
+        t0 = time.time()
+        proofs = [one_proof(i) for i in range(inflight)]                 # loads the key (tables) on first use
+        log(f"[bench] rank {rank} {mode}: key load + first proofs {time.time() - t0:.1f}s")
+        assert all(p_.data == proofs[0].data for p_ in proofs)
+        run_steps(max(args.warmup, inflight))
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = ctxs[0].launch_count()
+        t0 = time.perf_counter()
+        proof = run_steps(args.steps)                                     # e2e: host witness in, proof bytes out, every step
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        launches = ctxs[0].launch_count() - launches0
+        timings = ctxs[0].last_timings()
+        res = {"mode": mode, "proof": proof, "launches": launches, "timings": timings, "e2e_s": e2e_s, "ctxs": ctxs}
+        per_step = world if mode == 'replicas' else 1                    # replicas: every rank proves its own copy
+        res["e2e_value"] = per_step * args.steps / e2e_s
+        if not sharded:
+            # device-resident: witness already in HBM, CUDA events inside the library, same number in flight
+            barrier()
+            per = [args.steps // inflight + (1 if i < args.steps % inflight else 0) for i in range(inflight)]
+            tot = [0.0] * inflight
+            def dev_worker(i):
+                if per[i]:
+                    tot[i] = ctxs[i].bench_device(pk, cm, per[i]) * per[i]
+            threads(dev_worker, inflight)
+            dev_ms = max_over_ranks(max(tot) / args.steps)
+            barrier()
+            res["value"] = per_step * 1e3 / dev_ms
+            res["latency_ms"] = ctxs[0].bench_device(pk, cm, 5)
+            barrier()
+        else:
+            res["value"] = res["e2e_value"]
+            t0 = time.perf_counter()
+            for _ in range(5):
+                one_proof(0)
+            barrier()
+            res["latency_ms"] = max_over_ranks((time.perf_counter() - t0) / 5 * 1e3)
+        res["clocks"] = sampler.stop() if rank == 0 else None
+        return res
+
+    main_mode = 'single' if world == 1 else args.mode
+    main = measure(main_mode)
+    proof = main["proof"]
+    ctx = main["ctxs"][0]
+
+    # correctness gate: closed-form discrete logs of the unique proof under the trapdoor
+    if rank == 0 and not args.skip_check:
+        from circom_compat_b200.zkey import Q_MOD
+        h = fr_from_mont(CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wms[0], setup_ctx))
+        da, db, dc = synth.expected_proof_dlogs(td, w, h, R_FIX, S_FIX, circ.num_inputs)
+        ea = setup_ctx.fixed_base_g1(synth._ints_to_limbs([da, dc])); eb = setup_ctx.fixed_base_g2(synth._ints_to_limbs([db]))
+        qinv = pow(1 << 256, -1, Q_MOD)
+        def canon(a): return [int.from_bytes(np.ascontiguousarray(a).tobytes()[i:i + 32], 'little') * qinv % Q_MOD for i in range(0, a.size * 8, 32)]
+        exp = canon(ea[0]) + canon(eb[0]) + canon(ea[1])
+        got = [int.from_bytes(proof.data[i:i + 32], 'little') for i in range(0, 256, 32)]
+        assert exp == got, "proof does not match the trapdoor's closed-form expectation"
+        log("[bench] proof matches the trapdoor closed form")
+
+    roof, extra = None, {}
     if rank == 0:
         peak, how = measured_peaks()
+        shard_div = world if main_mode == 'sharded' else 1
         # dominant kernel: msm_accumulate_kernel<G1> on the H query (n = domain bases / scalars), run alone
         msm_ms, acc_ms = ctx.bench_msm(pk, cm, 0, 5)
-        nH = pk.domain_size // (world if sharded else 1)
-        alg = nH * 96.0
+        alg = pk.domain_size // shard_div * 96.0
         roof = {"bound": "hbm", "kernel": "msm_accumulate_kernel<G1> (H query)", "achieved": alg / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": how, "algorithmic_bytes": alg,
+                "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": 2.17e9 / shard_div, "peak_source": how, "algorithmic_bytes": alg,
                 "kernel_ms": acc_ms, "whole_msm_ms": msm_ms,
-                "note": "254-bit Pippenger is bound by the INT32 IMAD pipe, not HBM (DESIGN.md section 5); see profiles/ for ncu pipe utilisation"}
+                "traffic_source": "ncu dram__bytes_read+write per launch at 2^20 (profiles/r1_first_ncu_summary.txt)",
+                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, 87.5 % busy in ncu, not by HBM (DESIGN.md section 5)"}
         g2_ms, g2_acc = ctx.bench_msm(pk, cm, 4, 3)
-        extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / (world if sharded else 1) * 160.0 / (g2_acc * 1e-3) / 1e9}
-        extra["phase_ms_last_proof"] = timings
-        extra["in_flight"] = inflight
-        if not sharded:
-            extra["single_proof_latency_ms"] = lat
+        extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / shard_div * 160.0 / (g2_acc * 1e-3) / 1e9}
+        extra["phase_ms_last_proof"] = main["timings"]
+        extra["in_flight"] = len(main["ctxs"])
+        extra["single_proof_latency_ms"] = main["latency_ms"]
+    for c_ in main["ctxs"]:
+        c_.close()
+
+    other = None
+    if world > 1 and not args.one_mode:
+        other_mode = 'sharded' if main_mode == 'replicas' else 'replicas'
+        o_ = measure(other_mode)
+        assert o_["proof"].data == proof.data, "sharded and whole proofs differ"
+        other = {"mode": other_mode, "value": o_["value"], "e2e_value": o_["e2e_value"], "unit": "proofs/s", "latency_ms": o_["latency_ms"],
+                 "scaling": "strong" if other_mode == 'sharded' else "weak", "gpu_launches": o_["launches"]}
+        for c_ in o_["ctxs"]:
+            c_.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -298,25 +320,29 @@ def run_ours(args):
         assert ref == proof.data, "GPU proof bytes differ from the CPU oracle's"
         log(f"[bench] CPU oracle proof identical to the GPU proof; {dt:.2f}s on {cores} threads")
         cpu = {"value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
-               "sample": f"1 full proof of the same workload (same key, witness, r, s), oracle/cref.c C+OpenMP restatement of the ark-groth16 0.5 CPU path; proof bytes asserted identical",
+               "sample": "1 full proof of the same workload (same key, witness, r, s), oracle/cref.c C+OpenMP restatement of the ark-groth16 0.5 CPU path; proof bytes asserted identical",
                "phases_s": cref.last_phase_seconds()}
 
     if rank == 0:
         cfg = workload_config(args, circ)
-        cfg["in_flight"] = inflight
-        cfg["parallelism"] = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs + NCCL all-gather of 768 B partials" if sharded else f"{world} replicas")
+        cfg["in_flight"] = 1 if main_mode == "sharded" else inflight
+        cfg["parallelism"] = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs + one NCCL all-gather of 768 B partials per proof"
+                                                              if main_mode == 'sharded' else f"{world} replicas (one whole prover per GPU)")
+        sharded = main_mode == 'sharded'
+        value = main["value"]
+        per_step = world if main_mode == 'replicas' else 1
         out = {"metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 / value * proofs_per_step, "higher_is_better": True, "scaling": "strong" if sharded or world == 1 else "weak", "vs_baseline": None,
-               "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic", "config": cfg, "clocks": clocks,
-               "e2e": {"value": e2e_val, "unit": "proofs/s", "h2d_bytes_per_step": n_vars * 32 + (768 * world if sharded else 0),
-                       "d2h_bytes_per_step": 256 + (768 * (world + 1) if sharded else 0), "ms_per_step": 1e3 * e2e_s / args.steps},
-               "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+               "ms_per_step": 1e3 / value * per_step, "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak", "vs_baseline": None,
+               "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic", "config": cfg, "clocks": main["clocks"],
+               "e2e": {"value": main["e2e_value"], "unit": "proofs/s", "h2d_bytes_per_step": n_vars * 32 + (768 * world if sharded else 0),
+                       "d2h_bytes_per_step": 256 + (768 * (world + 1) if sharded else 0), "ms_per_step": 1e3 * main["e2e_s"] / args.steps},
+               "gpu_launches": main["launches"], "roofline": roof, "cpu_baseline": cpu}
         out.update(extra)
+        if other:
+            out["other_mode"] = other
         print(json.dumps(out), flush=True)
-    from circom_compat_b200 import release_all
     release_all()
-    for c_ in ctxs:
-        c_.close()
+    setup_ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -329,7 +355,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--log-n', type=int, default=20)
     ap.add_argument('--workload', default='chain', choices=['chain', 'circomlike'])
-    ap.add_argument('--mode', default='sharded', choices=['sharded', 'replicas'])
+    ap.add_argument('--mode', default='replicas', choices=['sharded', 'replicas'], help='N>1: headline mode (the other one is measured too, see other_mode)')
+    ap.add_argument('--one-mode', action='store_true', help='N>1: measure only --mode')
     ap.add_argument('--inflight', type=int, default=2, help='proofs in flight per GPU (one Context + host thread each)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--skip-check', action='store_true')

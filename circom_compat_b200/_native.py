@@ -61,7 +61,7 @@ def lib():
         L.b2g_matrices_free.argtypes = [vp]
         L.b2g_witness_map.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_uint32)]
         L.b2g_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
-        L.b2g_prove_partial.argtypes = [vp, vp, vp, vp, vp]
+        L.b2g_prove_partial.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_prove_finish.argtypes = [vp, vp, vp, i, vp, vp, vp]
         L.b2g_msm_g1.argtypes = [vp, vp, vp, sz, i, vp]
         L.b2g_msm_g2.argtypes = [vp, vp, vp, sz, i, vp]

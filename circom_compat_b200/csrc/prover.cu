@@ -46,6 +46,7 @@ struct b2g_ctx {
     fe *d_w = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
     size_t cap_w = 0, cap_n = 0;
     float last_ms[16] = {};
+    bool pre_valid = false; uint32_t pre_r[8] = {}, pre_s[8] = {};   // (r, s) whose glue_pre result sits in d_pre
 };
 
 struct b2g_pk {
@@ -334,6 +335,7 @@ static void launch_glue_pre(b2g_ctx* ctx, b2g_pk* pk, const void* r, const void*
     CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_post, 0));      // d_pre of the previous proof is no longer read
     glue_pre_kernel<<<1, 128, 0, ctx->st_glue>>>(pk->d_consts, rr, ss, ctx->d_pre);
     CUDA_CHECK(cudaEventRecord(ctx->ev_pre, ctx->st_glue));
+    memcpy(ctx->pre_r, rr.l, 32); memcpy(ctx->pre_s, ss.l, 32); ctx->pre_valid = true;
     g_launch_count += 1;
 }
 
@@ -552,10 +554,12 @@ int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const
     });
 }
 
-int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont, void* partial_out) {
+int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, void* partial_out) {
     return guarded([&] {
-        if (!ctx || !partial_out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (!ctx || !pk || !partial_out) throw_error(B2G_E_SHAPE, "null pointer");
         DevGuard g(ctx->device);
+        ctx->pre_valid = false;
+        if (r_canon && s_canon) launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
         cudaStream_t s0 = ctx->st[0];
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
@@ -572,7 +576,8 @@ int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int cou
         if (count < 1 || count > 64) throw_error(B2G_E_SHAPE, "partial count out of range");
         DevGuard g(ctx->device);
         cudaStream_t s0 = ctx->st[0];
-        launch_glue_pre(ctx, pk, r_canon, s_canon);
+        if (!(ctx->pre_valid && !memcmp(ctx->pre_r, r_canon, 32) && !memcmp(ctx->pre_s, s_canon, 32))) launch_glue_pre(ctx, pk, r_canon, s_canon);
+        ctx->pre_valid = false;
         CUDA_CHECK(cudaMemcpyAsync(ctx->d_partials_all, partials_all, (size_t)count * B2G_PARTIAL_BYTES, cudaMemcpyHostToDevice, s0));
         launch_glue_post(ctx, pk, ctx->d_partials_all, count, r_canon, s_canon, s0);
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));

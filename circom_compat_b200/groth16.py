@@ -252,11 +252,14 @@ class Groth16:
     # base-range sharded variant: every rank calls prove_partial, the 768-byte partials are all-gathered by the caller
     # (torch.distributed / NCCL), then every rank calls prove_finish and obtains the same proof.
     @staticmethod
-    def prove_partial(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, ctx: Context) -> np.ndarray:
+    def prove_partial(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, ctx: Context, r=None, s=None) -> np.ndarray:
+        """r, s are optional here: when given, the (r, s)-only scalar multiplications start alongside the MSMs."""
         w = _c(full_assignment)
         ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars)
         out = np.zeros(N.PARTIAL_BYTES, dtype=np.uint8)
-        N.check(N.lib().b2g_prove_partial(ctx._h, ph, mh, _ptr(w), _ptr(out)))
+        rr = _scalar_bytes(r) if r is not None else None
+        ss = _scalar_bytes(s) if s is not None else None
+        N.check(N.lib().b2g_prove_partial(ctx._h, ph, mh, _ptr(rr) if rr is not None else None, _ptr(ss) if ss is not None else None, _ptr(w), _ptr(out)))
         return out
 
     @staticmethod

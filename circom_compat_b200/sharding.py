@@ -24,7 +24,7 @@ def query_totals(n_vars: int, n_public: int, domain_size: int) -> dict:
     return {'h': (domain_size, 'h', 0), 'l': (n_vars - 1, 'w', 1), 'a': (n_vars - 1, 'w', 1), 'b1': (n_vars - 1, 'w', 1), 'b2': (n_vars - 1, 'w', 1)}
 
 
-def all_gather_partials(partial: np.ndarray, dist, device=None) -> np.ndarray:
+def all_gather_partials(partial: np.ndarray, dist, device=None, group=None) -> np.ndarray:
     """One all-gather of this rank's 768-byte partial; returns (world, 768) uint8 on the host."""
     import torch
     world = dist.get_world_size()
@@ -32,13 +32,13 @@ def all_gather_partials(partial: np.ndarray, dist, device=None) -> np.ndarray:
     if device is not None:
         mine = mine.to(device, non_blocking=True)
     out = torch.empty(world * PARTIAL_BYTES, dtype=torch.uint8, device=mine.device)
-    dist.all_gather_into_tensor(out, mine)
+    dist.all_gather_into_tensor(out, mine, group=group)
     return out.cpu().numpy().reshape(world, PARTIAL_BYTES)
 
 
-def prove_sharded(ctx, pk, matrices, w_mont, r, s, dist, device=None):
+def prove_sharded(ctx, pk, matrices, w_mont, r, s, dist, device=None, group=None):
     """One proof on a sharded context: partial MSMs -> all-gather -> identical fold on every rank."""
     from .groth16 import Groth16
-    part = Groth16.prove_partial(pk, matrices, w_mont, ctx)
-    allp = all_gather_partials(part, dist, device)
+    part = Groth16.prove_partial(pk, matrices, w_mont, ctx, r, s)
+    allp = all_gather_partials(part, dist, device, group)
     return Groth16.prove_finish(pk, allp, r, s, ctx)

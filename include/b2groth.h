@@ -111,7 +111,10 @@ B2G_API int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_cano
  * [H, L, A, B1] as G1 XYZZ (128 B each) followed by B2 as G2 XYZZ (256 B), mont.  b2g_prove_finish folds
  * shard_count partials in rank order and assembles the proof; every rank obtains identical bytes. */
 #define B2G_PARTIAL_BYTES 768
-B2G_API int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont, void* partial_out);
+/* r_canon / s_canon may be NULL; when given, the (r, s)-only part of the proof assembly (r*delta, s*delta, ...) is
+ * started here on a side stream so that b2g_prove_finish with the same (r, s) finds it done. */
+B2G_API int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont,
+                              void* partial_out);
 B2G_API int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int count, const void* r_canon,
                      const void* s_canon, uint8_t proof_out[256]);
 
