@@ -140,7 +140,7 @@ def run_reference(args):
            "data": "synthetic", "config": workload_config(args, circ),
            "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample, "phases_s": cref.last_phase_seconds()},
            "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, circ):
@@ -340,14 +340,27 @@ def run_ours(args):
         out.update(extra)
         if other:
             out["other_mode"] = other
-        print(json.dumps(out), flush=True)
+        emit(out)
     release_all()
     setup_ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line, on the process's real stdout (libraries such as NCCL print banners to fd 1)"""
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # anything else written to fd 1 goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
