@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libb2groth.so')
+LIB_PATH = os.environ.get('B2G_LIB') or os.path.join(_HERE, 'libb2groth.so')   # B2G_LIB: tuning builds only
 
 B2G_OK, B2G_E_DOMAIN, B2G_E_SHAPE, B2G_E_DEVICE, B2G_E_INPUT = 0, -1, -2, -3, -4
 PARTIAL_BYTES = 768

@@ -240,6 +240,124 @@ struct Fp {
     }
     static __device__ __forceinline__ fe sqr(const fe& a) { return mul(a, a); }
 
+    // ------------------------------------------------------------------ lazy-reduction building blocks (used by Fq2)
+    // t[0..15] = a * b as a plain 512-bit integer (a, b any 256-bit values).  Schoolbook on even/odd column accumulators:
+    // every 8-limb carry chain ends in a limb that so far holds at most a few carries, so one addc closes it.
+    static __device__ __forceinline__ void mul_wide(uint32_t* t, const fe& a, const fe& b) {
+        uint32_t ev[17], od[16];
+        #pragma unroll
+        for (int i = 0; i < 17; i++) ev[i] = 0;
+        #pragma unroll
+        for (int i = 0; i < 16; i++) od[i] = 0;
+        #pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            // even row i: a_even * b_i -> positions i.. (ev), a_odd * b_i -> positions i+1.. (od index i)
+            cmad4(&ev[i], ev[i + 8], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+            cmad4(&od[i], od[i + 8 < 16 ? i + 8 : 15], a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+            // odd row i+1: a_even * b -> positions i+1.. (od index i), a_odd * b -> positions i+2.. (ev)
+            cmad4(&od[i], od[i + 8 < 16 ? i + 8 : 15], a.l[0], a.l[2], a.l[4], a.l[6], b.l[i + 1]);
+            cmad4(&ev[i + 2], ev[i + 10 < 17 ? i + 10 : 16], a.l[1], a.l[3], a.l[5], a.l[7], b.l[i + 1]);
+        }
+        // t = ev + (od << 32)
+        t[0] = ev[0];
+        asm("add.cc.u32 %0, %15, %30;\n\t"
+            "addc.cc.u32 %1, %16, %31;\n\t"
+            "addc.cc.u32 %2, %17, %32;\n\t"
+            "addc.cc.u32 %3, %18, %33;\n\t"
+            "addc.cc.u32 %4, %19, %34;\n\t"
+            "addc.cc.u32 %5, %20, %35;\n\t"
+            "addc.cc.u32 %6, %21, %36;\n\t"
+            "addc.cc.u32 %7, %22, %37;\n\t"
+            "addc.cc.u32 %8, %23, %38;\n\t"
+            "addc.cc.u32 %9, %24, %39;\n\t"
+            "addc.cc.u32 %10, %25, %40;\n\t"
+            "addc.cc.u32 %11, %26, %41;\n\t"
+            "addc.cc.u32 %12, %27, %42;\n\t"
+            "addc.cc.u32 %13, %28, %43;\n\t"
+            "addc.u32 %14, %29, %44;"
+            : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+              "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+            : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]),
+              "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+              "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]),
+              "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+    }
+
+    // t -= u  (512-bit); returns the borrow mask (0xffffffff when t < u)
+    static __device__ __forceinline__ uint32_t sub_wide(uint32_t* t, const uint32_t* u) {
+        uint32_t br;
+        asm("sub.cc.u32 %0, %0, %17;\n\t"
+            "subc.cc.u32 %1, %1, %18;\n\t"
+            "subc.cc.u32 %2, %2, %19;\n\t"
+            "subc.cc.u32 %3, %3, %20;\n\t"
+            "subc.cc.u32 %4, %4, %21;\n\t"
+            "subc.cc.u32 %5, %5, %22;\n\t"
+            "subc.cc.u32 %6, %6, %23;\n\t"
+            "subc.cc.u32 %7, %7, %24;\n\t"
+            "subc.cc.u32 %8, %8, %25;\n\t"
+            "subc.cc.u32 %9, %9, %26;\n\t"
+            "subc.cc.u32 %10, %10, %27;\n\t"
+            "subc.cc.u32 %11, %11, %28;\n\t"
+            "subc.cc.u32 %12, %12, %29;\n\t"
+            "subc.cc.u32 %13, %13, %30;\n\t"
+            "subc.cc.u32 %14, %14, %31;\n\t"
+            "subc.cc.u32 %15, %15, %32;\n\t"
+            "subc.u32 %16, 0, 0;"
+            : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
+              "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15]), "=r"(br)
+            : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+              "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]));
+        return br;
+    }
+
+    // high half of t += p & mask  (adds p * 2^256 when mask is all ones)
+    static __device__ __forceinline__ void add_p_high(uint32_t* t, uint32_t mask) {
+        uint32_t m0 = P::P0 & mask, m1 = P::P1 & mask, m2 = P::P2 & mask, m3 = P::P3 & mask,
+                 m4 = P::P4 & mask, m5 = P::P5 & mask, m6 = P::P6 & mask, m7 = P::P7 & mask;
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(m6), "r"(m7));
+    }
+
+    // Montgomery reduction of a 512-bit t < p * 2^256: returns (t + M p) / 2^256 reduced once, i.e. in [0, p) when
+    // t < p^2 * 1 (result before the subtraction < t / 2^256 + p < 2p).
+    static __device__ __forceinline__ fe redc(const uint32_t* t) {
+        uint32_t x[8], e[8], carry = 0;
+        #pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = t[i];
+        #pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t m = x[0] * P::INV;
+            mul4(e, P::P1, P::P3, P::P5, P::P7, m);                 // positions 1..8
+            e[7] += carry;                                          // carry of the previous shift (position 8 -> 7 after it)
+            cmad4(x, e[7], P::P0, P::P2, P::P4, P::P6, m);          // x[0] becomes 0
+            // shift right by one limb: x'[k] = e[k] + x[k+1], x'[7] = e[7] + t[8+i]; carry -> next row
+            asm("add.cc.u32 %0, %9, %17;\n\t"
+                "addc.cc.u32 %1, %10, %18;\n\t"
+                "addc.cc.u32 %2, %11, %19;\n\t"
+                "addc.cc.u32 %3, %12, %20;\n\t"
+                "addc.cc.u32 %4, %13, %21;\n\t"
+                "addc.cc.u32 %5, %14, %22;\n\t"
+                "addc.cc.u32 %6, %15, %23;\n\t"
+                "addc.cc.u32 %7, %16, %24;\n\t"
+                "addc.u32 %8, 0, 0;"
+                : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(carry)
+                : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
+                  "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(t[8 + i]));
+        }
+        fe r;
+        #pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = x[i];
+        return reduce_once(r);                                      // carry is 0 here: the value is < 2p < 2^255
+    }
+
     static __device__ __forceinline__ fe from_canonical(const fe& a) { return mul(a, r2()); }
     static __device__ __forceinline__ fe to_canonical(const fe& a) {
         fe o = fe_zero(); o.l[0] = 1; return mul(a, o);
@@ -273,12 +391,35 @@ struct Fq2 {
     static __device__ __forceinline__ fe2 sub(const fe2& a, const fe2& b) { fe2 r; r.c0 = Fq::sub(a.c0, b.c0); r.c1 = Fq::sub(a.c1, b.c1); return r; }
     static __device__ __forceinline__ fe2 dbl(const fe2& a) { fe2 r; r.c0 = Fq::dbl(a.c0); r.c1 = Fq::dbl(a.c1); return r; }
     static __device__ __forceinline__ fe2 neg(const fe2& a) { fe2 r; r.c0 = Fq::neg(a.c0); r.c1 = Fq::neg(a.c1); return r; }
+    // Karatsuba over Fq2 with lazy reduction: three 512-bit products, two Montgomery reductions
+    //   c0 = a0 b0 - a1 b1,  c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1
     static __device__ __noinline__ fe2 mul(const fe2& a, const fe2& b) {
-        fe v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
-        fe s = Fq::add(a.c0, a.c1), t = Fq::add(b.c0, b.c1);
-        fe m = Fq::mul(s, t);
-        fe2 r; r.c0 = Fq::sub(v0, v1); r.c1 = Fq::sub(Fq::sub(m, v0), v1);
+        uint32_t v0[16], v1[16], v2[16];
+        Fq::mul_wide(v0, a.c0, b.c0);
+        Fq::mul_wide(v1, a.c1, b.c1);
+        fe sa = add_noreduce(a.c0, a.c1), sb = add_noreduce(b.c0, b.c1);      // < 2p < 2^255
+        Fq::mul_wide(v2, sa, sb);
+        Fq::sub_wide(v2, v0);
+        Fq::sub_wide(v2, v1);                                                 // a0 b1 + a1 b0 in [0, 2 p^2)
+        const uint32_t br = Fq::sub_wide(v0, v1);                             // a0 b0 - a1 b1 (mod 2^512)
+        Fq::add_p_high(v0, br);                                               // + p * 2^256 if negative: now in [0, p^2) or [p R - p^2, p R)
+        fe2 r; r.c0 = Fq::redc(v0); r.c1 = Fq::redc(v2);
         return r;
+    }
+    static __device__ __forceinline__ fe add_noreduce(const fe& a, const fe& b) {
+        fe s;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(s.l[0]), "=r"(s.l[1]), "=r"(s.l[2]), "=r"(s.l[3]), "=r"(s.l[4]), "=r"(s.l[5]), "=r"(s.l[6]), "=r"(s.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+        return s;
     }
     static __device__ __noinline__ fe2 sqr(const fe2& a) {
         fe s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);

@@ -107,8 +107,17 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const fe* __restrict__
 // Thread t owns sorted positions [t*chunk, (t+1)*chunk).  Buckets that lie entirely inside the run are written to
 // buckets[]; a run's first / last segment that belongs to a bucket crossing the run boundary goes to frag_first[t] /
 // frag_last[t].
+// occupancy targets: G1 runs 4 CTAs/SM at 126 registers; G2 sits at 174 registers, 1 % over the 3-CTA limit (170), so it
+// is capped there (ncu: 2 CTAs/SM left the IMAD pipe waiting on dependent-issue latency with 2 warps per scheduler)
+template <class F> struct AccOcc;
+template <> struct AccOcc<Fq> { static constexpr int MIN_CTAS = 4; };
+#ifndef B2G_G2_CTAS
+#define B2G_G2_CTAS 3
+#endif
+template <> struct AccOcc<Fq2> { static constexpr int MIN_CTAS = B2G_G2_CTAS; };
+
 template <class C, class F>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
                                       const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
                                       void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last) {
     using Pt = typename C::Pt; using Aff = typename C::Aff;
