@@ -101,6 +101,27 @@ def oracle_key(pk, cm):
     return za
 
 
+def physical_cores():
+    """hardware cores (not SMT threads): the OpenMP port runs ~3x slower oversubscribed on hyperthreads"""
+    try:
+        seen = set()
+        phys = core = None
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('physical id'):
+                phys = line.split(':')[1].strip()
+            elif line.startswith('core id'):
+                core = line.split(':')[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    seen.add((phys, core))
+                phys = core = None
+        if seen:
+            return len(seen)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def cpu_setup(circ):
     """proving key from the CPU oracle only (reference arm: none of our kernels anywhere)"""
     from circom_compat_b200 import synth
@@ -120,7 +141,7 @@ def run_reference(args):
     from oracle import cref
     from circom_compat_b200 import fr_to_mont
     cref.build()
-    cores = cref.lib().cref_max_threads()
+    cores = min(cref.lib().cref_max_threads(), physical_cores())
     circ, w = build_workload(args.log_n, args.workload)
     t0 = time.time()
     pk, _ = cpu_setup(circ)
@@ -128,10 +149,10 @@ def run_reference(args):
     log(f"[bench] CPU setup {time.time() - t0:.1f}s on {cores} threads")
     za, wm = oracle_key(pk, cm), fr_to_mont(w)
     for _ in range(args.warmup):
-        cref.prove(za, R_FIX, S_FIX, wm)
+        cref.prove(za, R_FIX, S_FIX, wm, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cref.prove(za, R_FIX, S_FIX, wm)
+        cref.prove(za, R_FIX, S_FIX, wm, nthreads=cores)
     dt = time.perf_counter() - t0
     val = args.steps / dt
     sample = f"{args.steps} full proofs of the {args.workload} 2^{args.log_n} workload, oracle/cref.c (C + OpenMP restatement of ark-groth16 0.5), {cores} threads"
@@ -312,10 +333,10 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu:
         from oracle import cref
         cref.build()
-        cores = cref.lib().cref_max_threads()
+        cores = min(cref.lib().cref_max_threads(), physical_cores())
         za = oracle_key(pk, cm)
         t0 = time.perf_counter()
-        ref = cref.prove(za, R_FIX, S_FIX, wm_np)
+        ref = cref.prove(za, R_FIX, S_FIX, wm_np, nthreads=cores)
         dt = time.perf_counter() - t0
         assert ref == proof.data, "GPU proof bytes differ from the CPU oracle's"
         log(f"[bench] CPU oracle proof identical to the GPU proof; {dt:.2f}s on {cores} threads")

@@ -81,7 +81,7 @@ struct Curve {
         E ppp = F::mul(p, pp);
         E qq = F::mul(acc.x, pp);
         E x3 = F::sub(F::sub(F::sqr(r), ppp), F::dbl(qq));
-        E y3 = F::sub(F::mul(r, F::sub(qq, x3)), F::mul(acc.y, ppp));
+        E y3 = F::mul_sub(r, F::sub(qq, x3), acc.y, ppp);
         acc.x = x3; acc.y = y3;
         acc.zz = F::mul(acc.zz, pp);
         acc.zzz = F::mul(acc.zzz, ppp);

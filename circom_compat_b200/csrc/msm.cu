@@ -42,19 +42,50 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const void* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ (1) digits + histogram
-__global__ void __launch_bounds__(256) msm_count_kernel(const fe* __restrict__ scalars, uint32_t n, int scalars_mont, int c, int nwin,
-                                 fe* __restrict__ canon_out, uint32_t* __restrict__ counts) {
+// (1a) scalars -> canonical integers (one Montgomery reduction each)
+__global__ void __launch_bounds__(256) msm_canon_kernel(const fe* __restrict__ scalars, uint32_t n, int scalars_mont, fe* __restrict__ canon_out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe k = fe_load_nc(&scalars[i]);
     if (scalars_mont) k = Fr::to_canonical(k);
     fe_store(&canon_out[i], k);
-    if (fe_is_zero(k)) return;
+}
+
+// raw c-bit window w of a canonical scalar held in global memory
+__device__ __forceinline__ uint32_t msm_window_bits(const uint32_t* __restrict__ k, int c, int w) {
+    const uint32_t off = (uint32_t)w * (uint32_t)c, limb = off >> 5, sh = off & 31u;
+    if (limb >= 8) return 0u;
+    uint64_t v = __ldg(&k[limb]);
+    if (limb + 1 < 8 && sh + (uint32_t)c > 32u) v |= (uint64_t)__ldg(&k[limb + 1]) << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+// Signed digit of window w without walking the whole carry chain (ark-ec make_digits semantics): the carry into window
+// w is 1 iff the window below holds >= 2^(c-1), 0 iff it holds < 2^(c-1) - 1, and only for the single value
+// 2^(c-1) - 1 does it depend on the next window down.
+__device__ __forceinline__ int32_t msm_digit_at(const uint32_t* __restrict__ k, int c, int w) {
+    const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < nwin; w++) {
-        int32_t d = msm_digit(k.l, c, w, carry);
-        if (d != 0) atomicAdd(&counts[(d < 0 ? -d : d) - 1], 1u);
+    for (int v = w - 1; v >= 0; v--) {
+        const uint32_t b = msm_window_bits(k, c, v);
+        if (b >= half) { carry = 1; break; }
+        if (b < half - 1) break;
     }
+    const uint32_t coef = msm_window_bits(k, c, w) + carry;
+    const uint32_t cout = (coef + half) >> c;
+    return (int32_t)coef - (int32_t)(cout << c);
+}
+
+// (1b) one thread per (window, scalar): bucket histogram.  Lanes of a warp that hit the same bucket (circom witnesses:
+// most wires are 0/1) are aggregated with match.any so that the hot buckets see one atomic per warp, not 32.
+__global__ void __launch_bounds__(256) msm_count_kernel(const fe* __restrict__ canon, uint32_t n, int c, int nwin, uint32_t* __restrict__ counts) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (uint32_t)(tid / n), i = (uint32_t)(tid % n);
+    int32_t d = 0;
+    if (w < (uint32_t)nwin) d = msm_digit_at(canon[i].l, c, (int)w);
+    const uint32_t b = d ? (uint32_t)(d < 0 ? -d : d) - 1u : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, b);
+    if (d != 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&counts[b], (uint32_t)__popc(peers));
 }
 
 // ------------------------------------------------------------------------------------------------ (2) exclusive scan (one CTA)
@@ -86,20 +117,22 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ (3) scatter
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const fe* __restrict__ canon, uint32_t n, uint32_t row_stride, int c, int nwin, const uint32_t* __restrict__ offsets,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    fe k = fe_load_nc(&canon[i]);
-    if (fe_is_zero(k)) return;
-    uint32_t carry = 0;
-    for (int w = 0; w < nwin; w++) {
-        int32_t d = msm_digit(k.l, c, w, carry);
-        if (d != 0) {
-            uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-            uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
-            entries[pos] = ((uint32_t)w * row_stride + i) | (d < 0 ? 0x80000000u : 0u);
-        }
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const fe* __restrict__ canon, uint32_t n, uint32_t row_stride, int c, int nwin,
+                                   const uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = (uint32_t)(tid / n), i = (uint32_t)(tid % n);
+    int32_t d = 0;
+    if (w < (uint32_t)nwin) d = msm_digit_at(canon[i].l, c, (int)w);
+    const uint32_t b = d ? (uint32_t)(d < 0 ? -d : d) - 1u : 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (d != 0 && (int)lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (d != 0) {
+        const uint32_t pos = offsets[b] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        entries[pos] = (w * row_stride + i) | (d < 0 ? 0x80000000u : 0u);
     }
 }
 
@@ -335,11 +368,13 @@ void msm_sort(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_
     if (n > s.cap_n || plan.nwin > s.cap_nwin || plan.nbuckets > s.cap_buckets || !s.entries) throw_error(B2G_E_SHAPE, "msm: sort scratch too small");
     const uint32_t nb = plan.nbuckets;
     CUDA_CHECK(cudaMemsetAsync(s.counts, 0, (size_t)nb * 4, st));
-    msm_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(scalars_dev, n, scalars_mont ? 1 : 0, plan.c, plan.nwin, s.scalars_canon, s.counts);
+    const unsigned pair_blocks = (unsigned)(((uint64_t)n * plan.nwin + 255) / 256);
+    msm_canon_kernel<<<(n + 255) / 256, 256, 0, st>>>(scalars_dev, n, scalars_mont ? 1 : 0, s.scalars_canon);
+    msm_count_kernel<<<pair_blocks, 256, 0, st>>>(s.scalars_canon, n, plan.c, plan.nwin, s.counts);
     msm_scan_kernel<<<1, 1024, 0, st>>>(s.counts, nb, s.offsets, s.cursor);
     // table rows are indexed w * plan.n + i (the table was built over plan.n bases, n may be shorter)
-    msm_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.scalars_canon, n, plan.n, plan.c, plan.nwin, s.offsets, s.cursor, s.entries);
-    g_launch_count += 3;
+    msm_scatter_kernel<<<pair_blocks, 256, 0, st>>>(s.scalars_canon, n, plan.n, plan.c, plan.nwin, s.offsets, s.cursor, s.entries);
+    g_launch_count += 4;
     CUDA_CHECK(cudaGetLastError());
 }
 
