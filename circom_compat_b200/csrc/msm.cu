@@ -322,7 +322,7 @@ void msm_free_table(MsmPlan& plan) { if (plan.table) cudaFree(plan.table); plan.
 
 void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, bool g2, bool with_sort) {
     s.g2 = g2; s.cap_n = n; s.cap_nwin = nwin; s.cap_buckets = nbuckets;
-    s.chunk = env_u32("B2G_MSM_CHUNK", 64);
+    s.chunk = env_u32(g2 ? "B2G_MSM_CHUNK_G2" : "B2G_MSM_CHUNK", env_u32("B2G_MSM_CHUNK", 64));
     const size_t pt = (g2 ? 4 * 64 : 4 * 32);
     const size_t nent = (size_t)n * nwin;
     const size_t nchunks = (nent + s.chunk - 1) / s.chunk + 1;
@@ -385,7 +385,7 @@ static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmS
     const uint32_t n = sorted.sorted_n;
     if (n == 0 || plan.table == nullptr) { CUDA_CHECK(cudaMemsetAsync(s.result, 0, ptb, st)); return; }
     if (plan.nbuckets > s.cap_buckets || n > s.cap_n || plan.nwin > s.cap_nwin) throw_error(B2G_E_SHAPE, "msm: accumulate scratch too small");
-    const uint32_t nb = plan.nbuckets, chunk = sorted.chunk;
+    const uint32_t nb = plan.nbuckets, chunk = s.chunk;
     CUDA_CHECK(cudaMemsetAsync(s.big_count, 0, 4, st));
     const uint64_t nent = (uint64_t)n * plan.nwin;
     const uint32_t nthreads = (uint32_t)((nent + chunk - 1) / chunk);

@@ -249,6 +249,12 @@ class Groth16:
         return Groth16.create_proof_with_reduction_and_matrices(pk, r, s, matrices, matrices.num_instance_variables,
                                                                 matrices.num_constraints, full_assignment, ctx)
 
+    @staticmethod
+    def generate_random_parameters_with_reduction(circuit, rng, ctx: Context = None) -> ProvingKey:
+        """Setup on the GPU (tests/groth16.rs:25 flow); `circuit` is a synth.Circuit (R1CS as coordinate lists)."""
+        from . import synth
+        return synth.generate_random_parameters_with_reduction(circuit, rng, ctx or default_context())
+
     # base-range sharded variant: every rank calls prove_partial, the 768-byte partials are all-gathered by the caller
     # (torch.distributed / NCCL), then every rank calls prove_finish and obtains the same proof.
     @staticmethod

@@ -190,8 +190,13 @@ class Trapdoor:
     ic_t: list
 
 
-def setup_scalars(circ: Circuit, seed: int = 0xB200) -> Trapdoor:
-    tau, alpha, beta, delta = sha_stream_fr(seed, 4, b'b2g-trapdoor')
+def setup_scalars(circ: Circuit, seed: int = 0xB200, trapdoor=None) -> Trapdoor:
+    """trapdoor = (tau, alpha, beta, gamma, delta) or None (derived from `seed`, gamma = 1)"""
+    if trapdoor is None:
+        tau, alpha, beta, delta = sha_stream_fr(seed, 4, b'b2g-trapdoor')
+        gamma = 1
+    else:
+        tau, alpha, beta, gamma, delta = (int(x) % R_MOD for x in trapdoor)
     n, m, li = circ.domain_size, circ.num_constraints, circ.num_inputs
     L = lagrange_at(n, tau)
     a_t = [0] * circ.n_vars; b_t = [0] * circ.n_vars; c_t = [0] * circ.n_vars
@@ -204,16 +209,19 @@ def setup_scalars(circ: Circuit, seed: int = 0xB200) -> Trapdoor:
     dinv = pow(delta, -1, R_MOD)
     abc = [(beta * a_t[i] + alpha * b_t[i] + c_t[i]) % R_MOD for i in range(circ.n_vars)]
     l_t = [x * dinv % R_MOD for x in abc[li:]]
-    return Trapdoor(tau, alpha, beta, delta, a_t, b_t, l_t, h_query_scalars(n, tau, dinv), abc[:li])
+    ginv = pow(gamma, -1, R_MOD)
+    td = Trapdoor(tau, alpha, beta, delta, a_t, b_t, l_t, h_query_scalars(n, tau, dinv), [x * ginv % R_MOD for x in abc[:li]])
+    td.gamma = gamma
+    return td
 
 
-def setup(ctx, circ: Circuit, seed: int = 0xB200):
+def setup(ctx, circ: Circuit, seed: int = 0xB200, trapdoor=None):
     """Returns (ProvingKey, Trapdoor); all group elements are produced on the GPU (b2g_fixed_base_*)."""
-    td = setup_scalars(circ, seed)
+    td = setup_scalars(circ, seed, trapdoor)
     nv = circ.n_vars
     g1_scalars = [td.alpha, td.beta, td.delta] + td.ic_t + td.a_t + td.b_t + td.l_t + td.h_t
     g1 = ctx.fixed_base_g1(_ints_to_limbs(g1_scalars))
-    g2 = ctx.fixed_base_g2(_ints_to_limbs([td.beta, 1, td.delta] + td.b_t))
+    g2 = ctx.fixed_base_g2(_ints_to_limbs([td.beta, getattr(td, 'gamma', 1), td.delta] + td.b_t))
     o = 3
     ic = g1[o:o + circ.num_inputs]; o += circ.num_inputs
     a_q = g1[o:o + nv]; o += nv
@@ -223,6 +231,17 @@ def setup(ctx, circ: Circuit, seed: int = 0xB200):
     pk = ProvingKey(nv, circ.num_inputs - 1, circ.domain_size, g1[0:1], g1[1:2], g2[0:1], g2[1:2], g1[2:3], g2[2:3],
                     ic, a_q, b1_q, g2[3:3 + nv], l_q, h_q)
     return pk, td
+
+
+def generate_random_parameters_with_reduction(circ: Circuit, rng, ctx):
+    """Groth16::<Bn254, CircomReduction>::generate_random_parameters_with_reduction(circuit, rng) as the reference's
+    tests call it (tests/groth16.rs:25): toxic waste (alpha, beta, gamma, delta, tau) drawn from `rng` (any object with
+    randrange), Lagrange evaluations on the host, every group element by fixed-base multiplication on the GPU, H query
+    from CircomReduction::h_query_scalars (src/circom/qap.rs:90-105).  Returns the ProvingKey only (the trapdoor is dropped)."""
+    trap = [rng.randrange(1, R_MOD) for _ in range(5)]
+    alpha, beta, gamma, delta, tau = trap
+    pk, _ = setup(ctx, circ, trapdoor=(tau, alpha, beta, gamma, delta))
+    return pk
 
 
 def expected_proof_dlogs(td: Trapdoor, w, h, r: int, s: int, num_inputs: int):

@@ -708,3 +708,56 @@ def trapdoor_expected_dlogs(sc, w, h, r, s, alpha, beta, delta, num_inputs):
     dc = (sum(x * y for x, y in zip(w[num_inputs:], sc['l'])) + sum(x * y for x, y in zip(h, sc['h']))
           + s * da + r * db - r * s % R_MOD * delta) % R_MOD
     return da, db, dc
+
+
+# ----------------------------------------------------------------------------- ark-serialize decompression (independent check)
+def _fq_sqrt(a):
+    # q = 3 mod 4
+    r = pow(a, (Q_MOD + 1) // 4, Q_MOD)
+    return r if r * r % Q_MOD == a % Q_MOD else None
+
+
+def _fq2_sqrt(a):
+    # complex method for u^2 = -1: sqrt(a0 + a1 u)
+    a0, a1 = a
+    if a1 == 0:
+        r = _fq_sqrt(a0)
+        if r is not None:
+            return (r, 0)
+        r = _fq_sqrt((-a0) % Q_MOD)
+        return (0, r)
+    alpha = _fq_sqrt((a0 * a0 + a1 * a1) % Q_MOD)
+    if alpha is None:
+        return None
+    inv2 = pow(2, -1, Q_MOD)
+    delta = (a0 + alpha) * inv2 % Q_MOD
+    x0 = _fq_sqrt(delta)
+    if x0 is None:
+        delta = (a0 - alpha) * inv2 % Q_MOD
+        x0 = _fq_sqrt(delta)
+    x1 = a1 * pow(2 * x0, -1, Q_MOD) % Q_MOD
+    return (x0, x1)
+
+
+def decompress_proof(data: bytes):
+    """Inverse of ark-serialize's compressed Proof<Bn254> encoding (flags: bit 7 = y is the larger root, bit 6 = infinity)."""
+    def g1(b):
+        flags = b[31] & 0xC0
+        x = int.from_bytes(bytes(b[:31]) + bytes([b[31] & 0x3F]), 'little')
+        if flags & 0x40:
+            return None
+        y = _fq_sqrt((x * x * x + 3) % Q_MOD)
+        neg = (Q_MOD - y) % Q_MOD
+        big, small = (y, neg) if y > neg else (neg, y)
+        return (x, big if flags & 0x80 else small)
+
+    def g2(b):
+        flags = b[63] & 0xC0
+        x = (int.from_bytes(b[:32], 'little'), int.from_bytes(bytes(b[32:63]) + bytes([b[63] & 0x3F]), 'little'))
+        if flags & 0x40:
+            return None
+        y = _fq2_sqrt(_Fq2.add(_Fq2.mul(_Fq2.sqr(x), x), G2_B))
+        neg = _Fq2.neg(y)
+        big, small = (y, neg) if (y[1], y[0]) > (neg[1], neg[0]) else (neg, y)
+        return (x, big if flags & 0x80 else small)
+    return g1(data[0:32]), g2(data[32:96]), g1(data[96:128])

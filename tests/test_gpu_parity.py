@@ -319,3 +319,23 @@ def test_headline_2p20_proof_closed_form(ctx):
     # the witness map at this size also satisfies the defining identity at a random point is covered by the closed form:
     # C's dlog contains (ab - c)(tau) through sum h_j * h_t[j]
     release(pk); release(cm)
+
+
+def test_gpu_setup_prove_verify_flow(ctx):
+    """tests/groth16.rs:11-41 flow on the GPU: generate_random_parameters_with_reduction -> prove -> verify (oracle pairing),
+    and the wrong-public-input negative of tests/groth16.rs:42-74."""
+    from circom_compat_b200 import Groth16, fr_to_mont, synth, release
+    circ, w = synth.circomlike_circuit(8)
+    rng = random.Random(1234)
+    pk = Groth16.generate_random_parameters_with_reduction(circ, rng, ctx)
+    cm = circ.matrices()
+    p = Groth16.prove(pk, cm, fr_to_mont(w), rng, ctx)
+    vk = o.ZKey()
+    def g1(a): return o._g1_from(np.ascontiguousarray(a).tobytes())
+    def g2(a): return o._g2_from(np.ascontiguousarray(a).tobytes())
+    vk.alpha_g1, vk.beta_g2, vk.gamma_g2, vk.delta_g2 = g1(pk.alpha_g1), g2(pk.beta_g2), g2(pk.gamma_g2), g2(pk.delta_g2)
+    vk.ic = [g1(x) for x in pk.gamma_abc_g1]
+    assert vk.gamma_g2 != o.G2_GEN                                   # gamma is random here, not 1
+    assert o.verify(vk, w[1:circ.num_inputs], (p.a, p.b, p.c))
+    assert not o.verify(vk, [(w[1] + 1) % o.R_MOD], (p.a, p.b, p.c))
+    release(pk); release(cm)

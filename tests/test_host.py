@@ -132,3 +132,32 @@ def test_cpp_read_zkey_matches_python_reader(name):
             for k in range(len(col)):
                 h = _fnv(val[k].tobytes(), h); h = _fnv(int(col[k]).to_bytes(4, 'little'), h)
         assert int(kv['coefs'], 16) == h
+
+
+# ------------------------------------------------------------------------------------------------ output formats
+def test_proof_formats(golden, test_zkey_bytes):
+    """Ethereum tuples (src/ethereum.rs) and ark-serialize encodings of a golden proof; the compressed form must
+    decompress (oracle, independent sqrt) back to the same points."""
+    from circom_compat_b200 import Proof, read_zkey
+    from circom_compat_b200 import ethereum as eth
+    case = golden['test_zkey']['proofs'][0]
+    p = Proof(bytes.fromhex(case['proof_hex']))
+    ep = eth.Proof.from_proof(p)
+    a, b, c_ = ep.as_tuple()
+    assert a == p.a and c_ == p.c
+    assert b == ([p.b[0][1], p.b[0][0]], [p.b[1][1], p.b[1][0]])          # c1 first (ethereum.rs:82-86)
+    assert len(ep.calldata()) == 256 and int.from_bytes(ep.calldata()[:32], 'big') == p.a[0]
+    comp = eth.serialize_compressed(ep)
+    assert len(comp) == 128
+    assert o.decompress_proof(comp) == (p.a, p.b, p.c)
+    unc = eth.serialize_uncompressed(ep)
+    assert len(unc) == 256 and unc == p.data                               # no point at infinity: identical to the ABI bytes
+    inf = eth.Proof(eth.G1(0, 0), ep.b, ep.c)
+    assert eth.serialize_compressed(inf)[31] == 0x40 and eth.serialize_uncompressed(inf)[63] == 0x40
+    pk, _ = read_zkey(test_zkey_bytes)
+    vk = eth.VerifyingKey.from_proving_key(pk)
+    z = o.read_zkey(test_zkey_bytes)
+    t = vk.as_tuple()
+    assert t[0] == z.alpha_g1 and t[1] == ([z.beta_g2[0][1], z.beta_g2[0][0]], [z.beta_g2[1][1], z.beta_g2[1][0]])
+    assert t[4] == [tuple(pt) for pt in z.ic]
+    assert eth.inputs([33]) == [33]
