@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get('B2G_LIB') or os.path.join(_HERE, 'libb2groth.so')   #
 
 B2G_OK, B2G_E_DOMAIN, B2G_E_SHAPE, B2G_E_DEVICE, B2G_E_INPUT = 0, -1, -2, -3, -4
 PARTIAL_BYTES = 768
+REDUCTION_CIRCOM, REDUCTION_LIBSNARK = 0, 1
 
 
 class B2gError(RuntimeError):
@@ -29,8 +30,8 @@ class PkDesc(C.Structure):
 
 
 class MatDesc(C.Structure):
-    _fields_ = [('num_constraints', C.c_uint32), ('num_inputs', C.c_uint32), ('n_vars', C.c_uint32), ('reserved', C.c_uint32)] + \
-               [(k, C.c_void_p) for k in ('a_rowptr', 'a_col', 'a_val', 'b_rowptr', 'b_col', 'b_val')]
+    _fields_ = [('num_constraints', C.c_uint32), ('num_inputs', C.c_uint32), ('n_vars', C.c_uint32), ('reduction', C.c_uint32)] + \
+               [(k, C.c_void_p) for k in ('a_rowptr', 'a_col', 'a_val', 'b_rowptr', 'b_col', 'b_val', 'c_rowptr', 'c_col', 'c_val')]
 
 
 EXPORTS = ['b2g_last_error', 'b2g_version', 'b2g_device_count', 'b2g_ctx_create', 'b2g_ctx_destroy', 'b2g_pk_load', 'b2g_pk_free',

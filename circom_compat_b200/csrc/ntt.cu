@@ -35,6 +35,25 @@ __global__ void ntt_setup_kernel(int logn, fe* __restrict__ pw, fe* __restrict__
     *ninv = Fr::inv(Fr::from_canonical(nn));
 }
 
+// LibsnarkReduction coset: pg[b] = g^(2^b), pgi[b] = g^-(2^b) for g = 5 (Fr::GENERATOR), zinv = (g^n - 1)^-1
+__global__ void ntt_setup_coset_kernel(int logn, fe* __restrict__ pg, fe* __restrict__ pgi, fe* __restrict__ zinv) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    fe five = fe_zero(); five.l[0] = 5;
+    fe g = Fr::from_canonical(five), gi = Fr::inv(g);
+    for (int b = 0; b <= logn; b++) { pg[b] = g; pgi[b] = gi; if (b < logn) { g = Fr::sqr(g); gi = Fr::sqr(gi); } }
+    // after the loop g = 5^(2^logn) = g^n
+    *zinv = Fr::inv(Fr::sub(g, Fr::one()));
+}
+
+// out[k] = scale * base^k for k < n, base^(2^b) given
+__global__ void __launch_bounds__(256) ntt_powers_kernel(int logn, const fe* __restrict__ pw, const fe* __restrict__ scale, fe* __restrict__ out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (1u << logn)) return;
+    fe acc = *scale;
+    for (int b = 0; b < logn; b++) if ((k >> b) & 1u) acc = Fr::mul(acc, pw[b]);
+    fe_store(&out[k], acc);
+}
+
 // tw[k] = omega_{2n}^k, ct[k] = n^-1 * omega_{2n}^k, k < n
 __global__ void __launch_bounds__(256) ntt_tables_kernel(int logn, const fe* __restrict__ pw, const fe* __restrict__ ninv,
                                                          fe* __restrict__ tw, fe* __restrict__ ct) {
@@ -52,7 +71,8 @@ __global__ void __launch_bounds__(256) ntt_tables_kernel(int logn, const fe* __r
 __global__ void __launch_bounds__(256) spmv_kernel(uint32_t n, uint32_t m, uint32_t num_inputs,
                             const uint32_t* __restrict__ a_rowptr, const uint32_t* __restrict__ a_col, const fe* __restrict__ a_val,
                             const uint32_t* __restrict__ b_rowptr, const uint32_t* __restrict__ b_col, const fe* __restrict__ b_val,
-                            const fe* __restrict__ w, fe* __restrict__ a, fe* __restrict__ b, fe* __restrict__ c) {
+                            const fe* __restrict__ w, fe* __restrict__ a, fe* __restrict__ b, fe* __restrict__ c,
+                            const uint32_t* __restrict__ c_rowptr, const uint32_t* __restrict__ c_col, const fe* __restrict__ c_val) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe ra = fe_zero(), rb = fe_zero(), rc = fe_zero();
@@ -66,7 +86,14 @@ __global__ void __launch_bounds__(256) spmv_kernel(uint32_t n, uint32_t m, uint3
             fe v = fe_load_nc(&b_val[k]); fe x = fe_load_nc(&w[b_col[k]]);
             rb = Fr::add(rb, fe_equal(v, one) ? x : Fr::mul(v, x));
         }
-        rc = Fr::mul(ra, rb);
+        if (c_rowptr) {                                           // LibsnarkReduction: c from the real C matrix
+            for (uint32_t k = c_rowptr[i]; k < c_rowptr[i + 1]; k++) {
+                fe v = fe_load_nc(&c_val[k]); fe x = fe_load_nc(&w[c_col[k]]);
+                rc = Fr::add(rc, fe_equal(v, one) ? x : Fr::mul(v, x));
+            }
+        } else {
+            rc = Fr::mul(ra, rb);                                 // CircomReduction: c = a o b (qap.rs:52-58)
+        }
     } else if (i < m + num_inputs) {
         ra = fe_load_nc(&w[i - m]);
     }
@@ -78,7 +105,8 @@ struct NttPassArgs {
     fe* vec[3];           // in-place vectors
     fe* out;              // pointwise result (h); may alias vec[0]
     const fe* tw;         // omega_{2n}^k, k < n
-    const fe* ct;         // n^-1 * omega_{2n}^k
+    const fe* ct;         // coset table applied by do_scale at the bit-reversed position: n^-1 * g^k
+    const fe* pw_scale;   // optional scalar multiplied into the pointwise result (LibsnarkReduction: 1 / Z(g))
     int logn, tl;         // tl = log2(tile)
     int sb, k;            // transform bits [sb, sb + k) of the element index
     int do_dif, do_scale, do_dit, pointwise;
@@ -172,8 +200,10 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
             } else if (vi == 0) { acc0 = x0; acc1 = x1; }
             else if (vi == 1) { acc0 = Fr::mul(acc0, x0); acc1 = Fr::mul(acc1, x1); }
             else {
-                fe_store(&A.out[g0], Fr::sub(acc0, x0));                  // h = a*b - c   (qap.rs:75-85)
-                if (half) fe_store(&A.out[g1], Fr::sub(acc1, x1));
+                fe r0 = Fr::sub(acc0, x0), r1 = Fr::sub(acc1, x1);        // h = a*b - c   (qap.rs:75-85)
+                if (A.pw_scale) { const fe z = *A.pw_scale; r0 = Fr::mul(r0, z); r1 = Fr::mul(r1, z); }
+                fe_store(&A.out[g0], r0);
+                if (half) fe_store(&A.out[g1], r1);
             }
         }
         __syncthreads();
@@ -181,17 +211,19 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
 }
 
 // out[bitrev(i)] = in[i] * (scale ? *scale : 1)
-__global__ void __launch_bounds__(256) bitrev_copy_kernel(const fe* __restrict__ in, fe* __restrict__ out, int logn, const fe* __restrict__ scale) {
+__global__ void __launch_bounds__(256) bitrev_copy_kernel(const fe* __restrict__ in, fe* __restrict__ out, int logn, const fe* __restrict__ scale,
+                                                          const fe* __restrict__ table) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (1u << logn)) return;
     uint32_t j = logn ? (__brev(i) >> (32 - logn)) : 0u;
     fe v = fe_load(&in[i]);
     if (scale) v = Fr::mul(v, *scale);
+    if (table) v = Fr::mul(v, fe_load_nc(&table[j]));          // per-coefficient factor, indexed by the natural position
     fe_store(&out[j], v);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st) {
+void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark) {
     // qap.rs:63-66 also needs the domain of size 2n, so n itself is limited to 2^27
     if (logn < 0 || logn > 27) throw_error(B2G_E_DOMAIN, "evaluation domain too large (PolynomialDegreeTooLarge)");
     d.logn = logn;
@@ -201,6 +233,14 @@ void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st) {
     CUDA_CHECK(cudaMalloc(&d.pw, 32 * sizeof(fe)));
     ntt_setup_kernel<<<1, 1, 0, st>>>(logn, d.pw, d.pw + 30);
     ntt_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logn, d.pw, d.pw + 30, d.tw, d.ct);
+    if (libsnark) {
+        CUDA_CHECK(cudaMalloc(&d.cg, n * sizeof(fe)));
+        CUDA_CHECK(cudaMalloc(&d.cginv, n * sizeof(fe)));
+        CUDA_CHECK(cudaMalloc(&d.zinv, 72 * sizeof(fe)));           // zinv | pg[32] | pgi[32]
+        ntt_setup_coset_kernel<<<1, 1, 0, st>>>(logn, d.zinv + 1, d.zinv + 36, d.zinv);
+        ntt_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logn, d.zinv + 1, d.pw + 30, d.cg);
+        ntt_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logn, d.zinv + 36, d.pw + 30, d.cginv);
+    }
     CUDA_CHECK(cudaGetLastError());
     // pass schedule: block pass (bits [0, tl)), then strided passes over the remaining bits, split evenly
     d.tl = logn < 10 ? logn : 10;
@@ -221,13 +261,16 @@ void ntt_domain_destroy(NttDomain& d) {
     if (d.tw) cudaFree(d.tw);
     if (d.ct) cudaFree(d.ct);
     if (d.pw) cudaFree(d.pw);
+    if (d.cg) cudaFree(d.cg);
+    if (d.cginv) cudaFree(d.cginv);
+    if (d.zinv) cudaFree(d.zinv);
     d = NttDomain();
 }
 
 static void launch_pass(const NttDomain& d, fe* v0, fe* v1, fe* v2, int nvec, fe* out, int pass, int dif, int scale, int dit, int pointwise,
-                        cudaStream_t st) {
+                        cudaStream_t st, const fe* coset_table = nullptr, const fe* pw_scale = nullptr) {
     NttPassArgs A;
-    A.vec[0] = v0; A.vec[1] = v1; A.vec[2] = v2; A.out = out; A.tw = d.tw; A.ct = d.ct;
+    A.vec[0] = v0; A.vec[1] = v1; A.vec[2] = v2; A.out = out; A.tw = d.tw; A.ct = coset_table ? coset_table : d.ct; A.pw_scale = pw_scale;
     A.logn = d.logn; A.tl = d.tl; A.sb = d.pass_sb[pass]; A.k = d.pass_k[pass];
     A.do_dif = dif; A.do_scale = scale; A.do_dit = dit; A.pointwise = pointwise;
     const uint32_t tile = 1u << d.tl;
@@ -247,16 +290,34 @@ void ntt_witness_transform(const NttDomain& d, fe* a, fe* b, fe* c, fe* out, cud
     CUDA_CHECK(cudaGetLastError());
 }
 
+// LibsnarkReduction::witness_map_from_matrices (ark-groth16 0.5.0 r1cs_to_qap.rs, the default QAP of Groth16<Bn254> used by
+// /root/reference/tests/groth16.rs): a, b, c (c from the real C matrix) -> coefficients -> evaluations on the coset
+// g*H (g = 5) -> (a*b - c) / Z(g) -> coset iFFT -> the n coefficients of h, natural order, in `out`.
+// Same kernels as the Circom map; the coset tables are cg / cginv, and the last inverse transform is a DIF pass set
+// followed by one bit-reversing copy that applies n^-1 g^-i.
+void ntt_witness_transform_libsnark(const NttDomain& d, fe* a, fe* b, fe* c, fe* scratch, fe* out, cudaStream_t st) {
+    if (!d.cg) throw_error(B2G_E_SHAPE, "matrices were not loaded for LibsnarkReduction");
+    for (int p = d.npass - 1; p >= 1; p--) launch_pass(d, a, b, c, 3, nullptr, p, 1, 0, 0, 0, st);
+    const bool single = d.npass == 1;
+    launch_pass(d, a, b, c, 3, scratch, 0, 1, 1, 1, single ? 1 : 0, st, d.cg, d.zinv);
+    for (int p = 1; p < d.npass; p++) launch_pass(d, a, b, c, 3, scratch, p, 0, 0, 1, p == d.npass - 1 ? 1 : 0, st, d.cg, d.zinv);
+    for (int p = d.npass - 1; p >= 0; p--) launch_pass(d, scratch, nullptr, nullptr, 1, nullptr, p, 1, 0, 0, 0, st);
+    const size_t n = (size_t)1 << d.logn;
+    bitrev_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scratch, out, d.logn, nullptr, d.cginv);
+    g_launch_count += 1;
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // plain natural-order (i)NTT of one vector (parity entry point b2g_ntt); tmp = scratch of n elements
 void ntt_plain(const NttDomain& d, fe* data, fe* tmp, bool inverse, cudaStream_t st) {
     const size_t n = (size_t)1 << d.logn;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (inverse) {
         for (int p = d.npass - 1; p >= 0; p--) launch_pass(d, data, nullptr, nullptr, 1, nullptr, p, 1, 0, 0, 0, st);
-        bitrev_copy_kernel<<<blocks, 256, 0, st>>>(data, tmp, d.logn, d.ct);        // ct[0] = n^-1
+        bitrev_copy_kernel<<<blocks, 256, 0, st>>>(data, tmp, d.logn, d.ct, nullptr);   // ct[0] = n^-1
         CUDA_CHECK(cudaMemcpyAsync(data, tmp, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
     } else {
-        bitrev_copy_kernel<<<blocks, 256, 0, st>>>(data, tmp, d.logn, nullptr);
+        bitrev_copy_kernel<<<blocks, 256, 0, st>>>(data, tmp, d.logn, nullptr, nullptr);
         CUDA_CHECK(cudaMemcpyAsync(data, tmp, n * sizeof(fe), cudaMemcpyDeviceToDevice, st));
         for (int p = 0; p < d.npass; p++) launch_pass(d, data, nullptr, nullptr, 1, nullptr, p, 0, 0, 1, 0, st);
     }
@@ -264,8 +325,9 @@ void ntt_plain(const NttDomain& d, fe* data, fe* tmp, bool inverse, cudaStream_t
 }
 
 void spmv_launch(uint32_t n, uint32_t m, uint32_t num_inputs, const uint32_t* a_rowptr, const uint32_t* a_col, const fe* a_val,
-                 const uint32_t* b_rowptr, const uint32_t* b_col, const fe* b_val, const fe* w, fe* a, fe* b, fe* c, cudaStream_t st) {
-    spmv_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, m, num_inputs, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val, w, a, b, c);
+                 const uint32_t* b_rowptr, const uint32_t* b_col, const fe* b_val, const fe* w, fe* a, fe* b, fe* c, cudaStream_t st,
+                 const uint32_t* c_rowptr, const uint32_t* c_col, const fe* c_val) {
+    spmv_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, m, num_inputs, a_rowptr, a_col, a_val, b_rowptr, b_col, b_val, w, a, b, c, c_rowptr, c_col, c_val);
     g_launch_count += 1;
     CUDA_CHECK(cudaGetLastError());
 }

@@ -62,8 +62,9 @@ struct b2g_mat {
     uint32_t m = 0, num_inputs = 0, n_vars = 0, n = 0;
     int logn = 0;
     NttDomain dom;
-    uint32_t *a_rowptr = nullptr, *a_col = nullptr, *b_rowptr = nullptr, *b_col = nullptr;
-    fe *a_val = nullptr, *b_val = nullptr;
+    uint32_t *a_rowptr = nullptr, *a_col = nullptr, *b_rowptr = nullptr, *b_col = nullptr, *c_rowptr = nullptr, *c_col = nullptr;
+    fe *a_val = nullptr, *b_val = nullptr, *c_val = nullptr;
+    uint32_t reduction = B2G_REDUCTION_CIRCOM;
 };
 
 namespace b2g {
@@ -287,6 +288,12 @@ static void ensure_scratch(b2g_ctx* ctx, const b2g_pk* pk) {
 }
 
 static void run_witness_map(b2g_ctx* ctx, b2g_mat* mat, cudaStream_t st) {
+    if (mat->reduction == B2G_REDUCTION_LIBSNARK) {
+        spmv_launch(mat->n, mat->m, mat->num_inputs, mat->a_rowptr, mat->a_col, mat->a_val, mat->b_rowptr, mat->b_col, mat->b_val,
+                    ctx->d_w, ctx->d_a, ctx->d_b, ctx->d_c, st, mat->c_rowptr, mat->c_col, mat->c_val);
+        ntt_witness_transform_libsnark(mat->dom, ctx->d_a, ctx->d_b, ctx->d_c, ctx->d_a, ctx->d_h, st);   // d_a doubles as scratch
+        return;
+    }
     spmv_launch(mat->n, mat->m, mat->num_inputs, mat->a_rowptr, mat->a_col, mat->a_val, mat->b_rowptr, mat->b_col, mat->b_val,
                 ctx->d_w, ctx->d_a, ctx->d_b, ctx->d_c, st);
     ntt_witness_transform(mat->dom, ctx->d_a, ctx->d_b, ctx->d_c, ctx->d_h, st);
@@ -297,7 +304,10 @@ static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
     if (pk->device != ctx->device || mat->device != ctx->device) throw_error(B2G_E_SHAPE, "handle belongs to another device");
     if (pk->shard_rank != ctx->shard_rank || pk->shard_count != ctx->shard_count) throw_error(B2G_E_SHAPE, "proving key was loaded for another shard");
     if (pk->n_vars != mat->n_vars) throw_error(B2G_E_SHAPE, "proving key and matrices disagree on n_vars");
-    if (pk->domain != mat->n) throw_error(B2G_E_SHAPE, "proving key domain_size != next_pow2(num_constraints + num_inputs)");
+    if (mat->reduction == B2G_REDUCTION_LIBSNARK) {
+        // arkworks keys carry domain - 1 H bases; msm_bigint pairs min(len) terms (the top coefficient of h is zero)
+        if (pk->domain + 1 != mat->n && pk->domain != mat->n) throw_error(B2G_E_SHAPE, "H query length must be domain_size - 1 (or domain_size) for LibsnarkReduction");
+    } else if (pk->domain != mat->n) throw_error(B2G_E_SHAPE, "proving key domain_size != next_pow2(num_constraints + num_inputs)");
     if (pk->n_public + 1 != mat->num_inputs) throw_error(B2G_E_SHAPE, "proving key n_public + 1 != num_inputs");
 }
 
@@ -322,7 +332,7 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
     run_witness_map(ctx, mat, s0);
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[11], s0));
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[0], s0));
-    msm_run(pk->plan[Q_H], ctx->scratch[Q_H], ctx->d_h + pk->lo[Q_H], pk->cnt[Q_H], true, s0);
+    msm_run(pk->plan[Q_H], ctx->scratch[Q_H], ctx->d_h + pk->lo[Q_H], pk->cnt[Q_H], true, s0);   // pairs min(#bases, #h) terms
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[1], s0));
     for (int q = 1; q < NQ; q++) CUDA_CHECK(cudaStreamWaitEvent(s0, ctx->ev_done[q], 0));
 }
@@ -479,6 +489,12 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
         const uint32_t m = d->num_constraints;
         const uint32_t annz = d->a_rowptr[m], bnnz = d->b_rowptr[m];
         if ((annz && (!d->a_col || !d->a_val)) || (bnnz && (!d->b_col || !d->b_val))) throw_error(B2G_E_SHAPE, "null matrix arrays");
+        if (d->reduction > B2G_REDUCTION_LIBSNARK) throw_error(B2G_E_SHAPE, "unknown reduction");
+        const bool libsnark = d->reduction == B2G_REDUCTION_LIBSNARK;
+        if (libsnark && !d->c_rowptr) throw_error(B2G_E_SHAPE, "LibsnarkReduction needs the C matrix");
+        const uint32_t cnnz = libsnark ? d->c_rowptr[m] : 0;
+        if (cnnz && (!d->c_col || !d->c_val)) throw_error(B2G_E_SHAPE, "null matrix arrays");
+        for (uint32_t k = 0; k < cnnz; k++) if (d->c_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix C column index out of range");
         for (uint32_t k = 0; k < annz; k++) if (d->a_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix A column index out of range");
         for (uint32_t k = 0; k < bnnz; k++) if (d->b_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix B column index out of range");
         DevGuard g(ctx->device);
@@ -491,7 +507,13 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
         mat->b_col = dev_upload<uint32_t>(d->b_col, (size_t)bnnz * 4, st);
         mat->a_val = dev_upload<fe>(d->a_val, (size_t)annz * 32, st);
         mat->b_val = dev_upload<fe>(d->b_val, (size_t)bnnz * 32, st);
-        ntt_domain_create(mat->dom, logn, st);
+        mat->reduction = d->reduction;
+        if (libsnark) {
+            mat->c_rowptr = dev_upload<uint32_t>(d->c_rowptr, ((size_t)m + 1) * 4, st);
+            mat->c_col = dev_upload<uint32_t>(d->c_col, (size_t)cnnz * 4, st);
+            mat->c_val = dev_upload<fe>(d->c_val, (size_t)cnnz * 32, st);
+        }
+        ntt_domain_create(mat->dom, logn, st, libsnark);
         g_launch_count += 2;
         CUDA_CHECK(cudaStreamSynchronize(st));
         *out = mat;
@@ -504,7 +526,8 @@ int b2g_matrices_free(b2g_mat* mat) {
         DevGuard g(mat->device);
         cudaDeviceSynchronize();
         ntt_domain_destroy(mat->dom);
-        for (void* p : {(void*)mat->a_rowptr, (void*)mat->a_col, (void*)mat->b_rowptr, (void*)mat->b_col, (void*)mat->a_val, (void*)mat->b_val}) if (p) cudaFree(p);
+        for (void* p : {(void*)mat->a_rowptr, (void*)mat->a_col, (void*)mat->b_rowptr, (void*)mat->b_col, (void*)mat->a_val, (void*)mat->b_val,
+                        (void*)mat->c_rowptr, (void*)mat->c_col, (void*)mat->c_val}) if (p) cudaFree(p);
         delete mat;
     });
 }

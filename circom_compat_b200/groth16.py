@@ -79,13 +79,19 @@ class Context:
             _PK_HANDLES[key] = (h, pk)
         return _PK_HANDLES[key][0]
 
-    def mat_handle(self, m: ConstraintMatrices, n_vars: int):
-        key = (id(m), self.device, n_vars)
+    def mat_handle(self, m: ConstraintMatrices, n_vars: int, reduction: int = N.REDUCTION_CIRCOM):
+        key = (id(m), self.device, n_vars, reduction)
         if key not in _MAT_HANDLES:
             d = N.MatDesc()
-            d.num_constraints, d.num_inputs, d.n_vars = m.num_constraints, m.num_instance_variables, n_vars
+            d.num_constraints, d.num_inputs, d.n_vars, d.reduction = m.num_constraints, m.num_instance_variables, n_vars, reduction
             keep = [_c(m.a[0], np.uint32), _c(m.a[1], np.uint32), _c(m.a[2]), _c(m.b[0], np.uint32), _c(m.b[1], np.uint32), _c(m.b[2])]
-            for name, arr in zip(('a_rowptr', 'a_col', 'a_val', 'b_rowptr', 'b_col', 'b_val'), keep):
+            names = ['a_rowptr', 'a_col', 'a_val', 'b_rowptr', 'b_col', 'b_val']
+            if reduction == N.REDUCTION_LIBSNARK:
+                if m.c is None:
+                    raise ValueError("LibsnarkReduction needs the C matrix (R1CS route); zkey matrices have none")
+                keep += [_c(m.c[0], np.uint32), _c(m.c[1], np.uint32), _c(m.c[2])]
+                names += ['c_rowptr', 'c_col', 'c_val']
+            for name, arr in zip(names, keep):
                 setattr(d, name, arr.ctypes.data if arr.size else None)
             h = C.c_void_p()
             N.check(N.lib().b2g_matrices_load(self._h, C.byref(d), C.byref(h)))
@@ -202,15 +208,16 @@ def _scalar_bytes(v) -> np.ndarray:
 
 class CircomReduction:
     """R1CSToQAP implementation selected by Groth16<Bn254, CircomReduction> (src/circom/qap.rs:12-14)."""
+    ID = N.REDUCTION_CIRCOM
 
-    @staticmethod
-    def witness_map_from_matrices(matrices: ConstraintMatrices, num_inputs: int, num_constraints: int, full_assignment, ctx: Context = None) -> np.ndarray:
+    @classmethod
+    def witness_map_from_matrices(cls, matrices: ConstraintMatrices, num_inputs: int, num_constraints: int, full_assignment, ctx: Context = None) -> np.ndarray:
         ctx = ctx or default_context()
         if num_inputs != matrices.num_instance_variables or num_constraints != matrices.num_constraints:
             raise ValueError("num_inputs / num_constraints disagree with the matrices")
         w = _c(full_assignment)
         n_vars = w.size // 4
-        mh = ctx.mat_handle(matrices, n_vars)
+        mh = ctx.mat_handle(matrices, n_vars, cls.ID)
         n = 1
         while n < num_constraints + num_inputs:
             n <<= 1
@@ -221,39 +228,46 @@ class CircomReduction:
         return h
 
 
+class LibsnarkReduction(CircomReduction):
+    """ark-groth16's default R1CSToQAP (`Groth16<Bn254>` in /root/reference/tests/groth16.rs:9,25-35): h = coefficients of
+    (a*b - c)/Z, c from the real C matrix; keys from generate_random_parameters_with_reduction carry domain_size - 1 H bases."""
+    ID = N.REDUCTION_LIBSNARK
+
+
 class Groth16:
-    """Groth16::<Bn254, CircomReduction>."""
+    """Groth16::<Bn254, QAP>; QAP = CircomReduction (snarkjs keys, default here) or LibsnarkReduction (arkworks keys)."""
 
     @staticmethod
     def create_proof_with_reduction_and_matrices(pk: ProvingKey, r, s, matrices: ConstraintMatrices, num_inputs: int,
-                                                 num_constraints: int, full_assignment, ctx: Context = None) -> Proof:
+                                                 num_constraints: int, full_assignment, ctx: Context = None, reduction=CircomReduction) -> Proof:
         ctx = ctx or default_context()
         if num_inputs != matrices.num_instance_variables or num_constraints != matrices.num_constraints:
             raise ValueError("num_inputs / num_constraints disagree with the matrices")
         w = _c(full_assignment)
         if w.size // 4 != pk.n_vars:
             raise ValueError("full_assignment length != n_vars")
-        ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars)
+        ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars, reduction.ID)
         rr, ss = _scalar_bytes(r), _scalar_bytes(s)
         out = np.zeros(256, dtype=np.uint8)
         N.check(N.lib().b2g_prove(ctx._h, ph, mh, _ptr(rr), _ptr(ss), _ptr(w), _ptr(out)))
         return Proof(out.tobytes())
 
     @staticmethod
-    def prove(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, rng, ctx: Context = None) -> Proof:
+    def prove(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, rng, ctx: Context = None, reduction=CircomReduction) -> Proof:
         """Draws r then s like create_random_proof_with_reduction (ark-groth16 0.5.0); rng is any object with
         randrange (e.g. random.Random / secrets.SystemRandom).  NB: arkworks' Fr::rand interprets the sampled limbs
         as a Montgomery residue; the distribution is uniform either way."""
         r = rng.randrange(R_MOD)
         s = rng.randrange(R_MOD)
         return Groth16.create_proof_with_reduction_and_matrices(pk, r, s, matrices, matrices.num_instance_variables,
-                                                                matrices.num_constraints, full_assignment, ctx)
+                                                                matrices.num_constraints, full_assignment, ctx, reduction)
 
     @staticmethod
-    def generate_random_parameters_with_reduction(circuit, rng, ctx: Context = None) -> ProvingKey:
+    def generate_random_parameters_with_reduction(circuit, rng, ctx: Context = None, reduction=CircomReduction) -> ProvingKey:
         """Setup on the GPU (tests/groth16.rs:25 flow); `circuit` is a synth.Circuit (R1CS as coordinate lists)."""
         from . import synth
-        return synth.generate_random_parameters_with_reduction(circuit, rng, ctx or default_context())
+        flavour = 'libsnark' if reduction.ID == N.REDUCTION_LIBSNARK else 'circom'
+        return synth.generate_random_parameters_with_reduction(circuit, rng, ctx or default_context(), flavour)
 
     # base-range sharded variant: every rank calls prove_partial, the 768-byte partials are all-gathered by the caller
     # (torch.distributed / NCCL), then every rank calls prove_finish and obtains the same proof.

@@ -80,13 +80,17 @@ class Circuit:
             n <<= 1
         return n
 
-    def matrices(self) -> ConstraintMatrices:
-        """ConstraintMatrices as read_zkey would return them (a, b only; src/zkey.rs:181-193)."""
+    def matrices(self, with_c: bool = False) -> ConstraintMatrices:
+        """ConstraintMatrices as read_zkey returns them (a, b only; src/zkey.rs:181-193), or with c as
+        ConstraintSystem::to_matrices() does on the R1CS route (with_c, needed by LibsnarkReduction)."""
         m = self.num_constraints
         mats = []
-        for rows, cols, vals in (self.A, self.B):
+        for rows, cols, vals in (self.A, self.B, self.C)[:3 if with_c else 2]:
             mats.append(csr_from_coo(np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.uint32), _to_mont_limbs(vals), m))
-        return ConstraintMatrices(self.num_inputs, self.n_vars - self.num_inputs, m, len(mats[0][1]), len(mats[1][1]), 0, mats[0], mats[1])
+        cm = ConstraintMatrices(self.num_inputs, self.n_vars - self.num_inputs, m, len(mats[0][1]), len(mats[1][1]), 0, mats[0], mats[1])
+        if with_c:
+            cm.c = mats[2]; cm.c_num_non_zero = len(mats[2][1])
+        return cm
 
 
 def chain_circuit(n_vars: int) -> Circuit:
@@ -190,7 +194,17 @@ class Trapdoor:
     ic_t: list
 
 
-def setup_scalars(circ: Circuit, seed: int = 0xB200, trapdoor=None) -> Trapdoor:
+def h_query_scalars_libsnark(n: int, tau: int, delta_inv: int):
+    """LibsnarkReduction::h_query_scalars (ark-groth16 0.5.0): tau^i * Z(tau) / delta for i < n - 1"""
+    zt = (pow(tau, n, R_MOD) - 1) * delta_inv % R_MOD
+    out, p = [], 1
+    for _ in range(n - 1):
+        out.append(p * zt % R_MOD)
+        p = p * tau % R_MOD
+    return out
+
+
+def setup_scalars(circ: Circuit, seed: int = 0xB200, trapdoor=None, flavour: str = 'circom') -> Trapdoor:
     """trapdoor = (tau, alpha, beta, gamma, delta) or None (derived from `seed`, gamma = 1)"""
     if trapdoor is None:
         tau, alpha, beta, delta = sha_stream_fr(seed, 4, b'b2g-trapdoor')
@@ -210,14 +224,16 @@ def setup_scalars(circ: Circuit, seed: int = 0xB200, trapdoor=None) -> Trapdoor:
     abc = [(beta * a_t[i] + alpha * b_t[i] + c_t[i]) % R_MOD for i in range(circ.n_vars)]
     l_t = [x * dinv % R_MOD for x in abc[li:]]
     ginv = pow(gamma, -1, R_MOD)
-    td = Trapdoor(tau, alpha, beta, delta, a_t, b_t, l_t, h_query_scalars(n, tau, dinv), [x * ginv % R_MOD for x in abc[:li]])
+    h_t = h_query_scalars(n, tau, dinv) if flavour == 'circom' else h_query_scalars_libsnark(n, tau, dinv)
+    td = Trapdoor(tau, alpha, beta, delta, a_t, b_t, l_t, h_t, [x * ginv % R_MOD for x in abc[:li]])
     td.gamma = gamma
     return td
 
 
-def setup(ctx, circ: Circuit, seed: int = 0xB200, trapdoor=None):
-    """Returns (ProvingKey, Trapdoor); all group elements are produced on the GPU (b2g_fixed_base_*)."""
-    td = setup_scalars(circ, seed, trapdoor)
+def setup(ctx, circ: Circuit, seed: int = 0xB200, trapdoor=None, flavour: str = 'circom'):
+    """Returns (ProvingKey, Trapdoor); all group elements are produced on the GPU (b2g_fixed_base_*).
+    flavour 'circom' = snarkjs keys (CircomReduction H query), 'libsnark' = arkworks keys (domain - 1 H bases)."""
+    td = setup_scalars(circ, seed, trapdoor, flavour)
     nv = circ.n_vars
     g1_scalars = [td.alpha, td.beta, td.delta] + td.ic_t + td.a_t + td.b_t + td.l_t + td.h_t
     g1 = ctx.fixed_base_g1(_ints_to_limbs(g1_scalars))
@@ -227,20 +243,20 @@ def setup(ctx, circ: Circuit, seed: int = 0xB200, trapdoor=None):
     a_q = g1[o:o + nv]; o += nv
     b1_q = g1[o:o + nv]; o += nv
     l_q = g1[o:o + nv - circ.num_inputs]; o += nv - circ.num_inputs
-    h_q = g1[o:o + circ.domain_size]
-    pk = ProvingKey(nv, circ.num_inputs - 1, circ.domain_size, g1[0:1], g1[1:2], g2[0:1], g2[1:2], g1[2:3], g2[2:3],
+    h_q = g1[o:o + len(td.h_t)]
+    pk = ProvingKey(nv, circ.num_inputs - 1, len(td.h_t), g1[0:1], g1[1:2], g2[0:1], g2[1:2], g1[2:3], g2[2:3],
                     ic, a_q, b1_q, g2[3:3 + nv], l_q, h_q)
     return pk, td
 
 
-def generate_random_parameters_with_reduction(circ: Circuit, rng, ctx):
+def generate_random_parameters_with_reduction(circ: Circuit, rng, ctx, flavour: str = 'circom'):
     """Groth16::<Bn254, CircomReduction>::generate_random_parameters_with_reduction(circuit, rng) as the reference's
     tests call it (tests/groth16.rs:25): toxic waste (alpha, beta, gamma, delta, tau) drawn from `rng` (any object with
     randrange), Lagrange evaluations on the host, every group element by fixed-base multiplication on the GPU, H query
     from CircomReduction::h_query_scalars (src/circom/qap.rs:90-105).  Returns the ProvingKey only (the trapdoor is dropped)."""
     trap = [rng.randrange(1, R_MOD) for _ in range(5)]
     alpha, beta, gamma, delta, tau = trap
-    pk, _ = setup(ctx, circ, trapdoor=(tau, alpha, beta, gamma, delta))
+    pk, _ = setup(ctx, circ, trapdoor=(tau, alpha, beta, gamma, delta), flavour=flavour)
     return pk
 
 

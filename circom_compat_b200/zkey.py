@@ -62,6 +62,7 @@ class ConstraintMatrices:
     c_num_non_zero: int
     a: tuple                        # (rowptr u32[m+1], col u32[nnz], val u64[nnz,4] Montgomery)
     b: tuple
+    c: tuple = None                 # only on the R1CS route (LibsnarkReduction); the zkey route has none (zkey.rs:188-192)
     _device: dict = field(default_factory=dict, repr=False)
 
     @property

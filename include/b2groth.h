@@ -76,14 +76,23 @@ typedef struct {
     uint32_t num_constraints; /* m: rows kept (src/zkey.rs:171-175) */
     uint32_t num_inputs;      /* num_instance_variables = n_public + 1 (src/zkey.rs:182) */
     uint32_t n_vars;          /* length of the full assignment */
-    uint32_t reserved;
+    uint32_t reduction;       /* B2G_REDUCTION_CIRCOM (0) or B2G_REDUCTION_LIBSNARK (1): which R1CSToQAP the handle serves */
     const uint32_t* a_rowptr; /* m + 1 */
     const uint32_t* a_col;
     const void* a_val;        /* nnz x 32 B mont */
     const uint32_t* b_rowptr;
     const uint32_t* b_col;
     const void* b_val;
+    const uint32_t* c_rowptr; /* LibsnarkReduction only (the zkey route has no C matrix, src/zkey.rs:188-192); else NULL */
+    const uint32_t* c_col;
+    const void* c_val;
 } b2g_mat_desc;
+
+/* CircomReduction: snarkjs keys, H query of domain_size bases, h = (ab - c)(g w^j), g = omega_2n   (src/circom/qap.rs:23-88).
+ * LibsnarkReduction: arkworks-generated keys (the default QAP of Groth16<Bn254>, tests/groth16.rs:9,25-35), H query of
+ * domain_size - 1 bases [tau^i Z(tau)/delta], h = coefficients of (ab - c)/Z (ark-groth16 0.5.0 r1cs_to_qap.rs). */
+#define B2G_REDUCTION_CIRCOM 0
+#define B2G_REDUCTION_LIBSNARK 1
 
 B2G_API const char* b2g_last_error(void);
 B2G_API int b2g_version(void);
@@ -99,7 +108,7 @@ B2G_API int b2g_pk_free(b2g_pk* pk);
 B2G_API int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* desc, b2g_mat** out);
 B2G_API int b2g_matrices_free(b2g_mat* mat);
 
-/* h = witness map; w_mont = n_vars x 32 B (host); h_out = domain x 32 B mont, natural order (host). */
+/* h = witness map of the handle's reduction; w_mont = n_vars x 32 B (host); h_out = domain x 32 B mont, natural order (host). */
 B2G_API int b2g_witness_map(b2g_ctx* ctx, b2g_mat* mat, const void* w_mont, void* h_out, uint32_t* domain_size_out);
 
 /* 256-byte proof: A.x A.y B.x.c0 B.x.c1 B.y.c0 B.y.c1 C.x C.y, canon little-endian; infinity = zeros.

@@ -359,6 +359,38 @@ EXPORT int cref_witness_map(uint32_t m, uint32_t num_inputs, uint32_t n_vars,
     return log_n;
 }
 
+/* LibsnarkReduction::witness_map_from_matrices (ark-groth16 0.5.0 r1cs_to_qap.rs; default QAP of Groth16<Bn254>,
+ * /root/reference/tests/groth16.rs:9,25-35): coset offset g = Fr::GENERATOR = 5, c from the real C matrix,
+ * h = coset_ifft((a*b - c) / Z(g)).  h_out = n coefficients (Montgomery).  Returns log2(n). */
+EXPORT int cref_witness_map_libsnark(uint32_t m, uint32_t num_inputs,
+                                     const uint32_t* a_rowptr, const uint32_t* a_col, const uint64_t* a_val,
+                                     const uint32_t* b_rowptr, const uint32_t* b_col, const uint64_t* b_val,
+                                     const uint32_t* c_rowptr, const uint32_t* c_col, const uint64_t* c_val,
+                                     const uint64_t* w_mont, uint64_t* h_out, int nthreads) {
+    nthreads = nthreads_or_default(nthreads);
+    size_t need = (size_t)m + num_inputs, n = 1; int log_n = 0;
+    while (n < need) { n <<= 1; log_n++; }
+    if (log_n > 28) return -1;
+    const fe* w = (const fe*)w_mont;
+    fe* a = (fe*)calloc(n, sizeof(fe)); fe* b = (fe*)calloc(n, sizeof(fe)); fe* c = (fe*)calloc(n, sizeof(fe));
+    eval_rows(a, m, a_rowptr, a_col, (const fe*)a_val, w, nthreads);
+    eval_rows(b, m, b_rowptr, b_col, (const fe*)b_val, w, nthreads);
+    eval_rows(c, m, c_rowptr, c_col, (const fe*)c_val, w, nthreads);
+    for (uint32_t j = 0; j < num_inputs; j++) a[m + j] = w[j];
+    fe five = {{5, 0, 0, 0}}, g, ginv; fr_from_canon(&g, &five); fr_inv(&ginv, &g);
+    fe* vs[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) { fr_fft(vs[k], log_n, 1, nthreads); fr_distribute_powers(vs[k], n, &g, nthreads); fr_fft(vs[k], log_n, 0, nthreads); }
+    fe gn = g; for (int i = 0; i < log_n; i++) fr_mul(&gn, &gn, &gn);
+    fe z, zinv; fr_sub(&z, &gn, &FR_R1); fr_inv(&zinv, &z);
+    fe* h = (fe*)h_out;
+    #pragma omp parallel for num_threads(nthreads)
+    for (size_t i = 0; i < n; i++) { fe t; fr_mul(&t, &a[i], &b[i]); fr_sub(&t, &t, &c[i]); fr_mul(&h[i], &t, &zinv); }
+    fr_fft(h, log_n, 1, nthreads);
+    fr_distribute_powers(h, n, &ginv, nthreads);
+    free(a); free(b); free(c);
+    return log_n;
+}
+
 /* MSM over G1: bases 64 B each (Montgomery), scalars canonical 4xu64.  out = affine Montgomery (zeros = infinity). */
 EXPORT int cref_msm_g1(const uint64_t* bases, const uint64_t* scalars_canon, size_t n, uint64_t* out_xy, int nthreads) {
     g1_jac acc; g1_msm(&acc, (const g1_aff*)bases, scalars_canon, n, nthreads_or_default(nthreads));

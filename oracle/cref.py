@@ -116,6 +116,20 @@ def witness_map(m, num_inputs, n_vars, a_csr, b_csr, w_mont, nthreads: int = 0) 
     return h
 
 
+def witness_map_libsnark(m, num_inputs, a_csr, b_csr, c_csr, w_mont, nthreads: int = 0) -> np.ndarray:
+    n = 1
+    while n < m + num_inputs:
+        n <<= 1
+    h = np.zeros((n, 4), dtype=np.uint64)
+    w = np.ascontiguousarray(w_mont, dtype=np.uint64)
+    rc = lib().cref_witness_map_libsnark(C.c_uint32(m), C.c_uint32(num_inputs), _p(a_csr[0]), _p(a_csr[1]), _p(a_csr[2]),
+                                         _p(b_csr[0]), _p(b_csr[1]), _p(b_csr[2]), _p(c_csr[0]), _p(c_csr[1]), _p(c_csr[2]),
+                                         _p(w), _p(h), C.c_int(nthreads))
+    if rc < 0:
+        raise ValueError("PolynomialDegreeTooLarge")
+    return h
+
+
 def msm_g1(bases: np.ndarray, scalars_canon: np.ndarray, nthreads: int = 0):
     bases = np.ascontiguousarray(bases, dtype=np.uint64); sc = np.ascontiguousarray(scalars_canon, dtype=np.uint64)
     n = min(bases.size // 8, sc.size // 4)

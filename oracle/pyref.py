@@ -761,3 +761,59 @@ def decompress_proof(data: bytes):
         big, small = (y, neg) if (y[1], y[0]) > (neg[1], neg[0]) else (neg, y)
         return (x, big if flags & 0x80 else small)
     return g1(data[0:32]), g2(data[32:96]), g1(data[96:128])
+
+
+# ----------------------------------------------------------------------------- LibsnarkReduction + R1CS route
+def libsnark_witness_map_from_matrices(mat_a, mat_b, mat_c, num_inputs, num_constraints, w):
+    """LibsnarkReduction::witness_map_from_matrices, ark-groth16 0.5.0 r1cs_to_qap.rs (un-vendored; the default QAP of
+    `Groth16<Bn254>` used by /root/reference/tests/groth16.rs:9,25-35).  Restated: a, b, c evaluations (c from the real C
+    matrix) -> ifft -> coset fft with offset g = Fr::GENERATOR = 5 -> (a*b - c) / Z(g) -> coset ifft.  Returns the n
+    coefficients of h (the top one is 0)."""
+    n = domain_size_for(num_constraints + num_inputs)
+    a = [0] * n; b = [0] * n; c = [0] * n
+    for i in range(num_constraints):
+        a[i] = sum(k * w[j] for k, j in mat_a[i]) % R_MOD
+        b[i] = sum(k * w[j] for k, j in mat_b[i]) % R_MOD
+        c[i] = sum(k * w[j] for k, j in mat_c[i]) % R_MOD
+    for j in range(num_inputs):
+        a[num_constraints + j] = w[j] % R_MOD
+    g = FR_GENERATOR
+    for v in (a, b, c):
+        fft(v, inverse=True); distribute_powers(v, g); fft(v)
+    zinv = pow((pow(g, n, R_MOD) - 1) % R_MOD, -1, R_MOD)
+    ab = [(x * y - z) * zinv % R_MOD for x, y, z in zip(a, b, c)]
+    fft(ab, inverse=True)
+    distribute_powers(ab, pow(g, -1, R_MOD))
+    return ab
+
+
+def libsnark_h_query_scalars(n, t, delta_inverse):
+    """LibsnarkReduction::h_query_scalars: tau^i * Z(tau) / delta, i < n - 1"""
+    zt = (pow(t, n, R_MOD) - 1) * delta_inverse % R_MOD
+    return [pow(t, i, R_MOD) * zt % R_MOD for i in range(n - 1)]
+
+
+def read_r1cs(data: bytes):
+    """src/circom/r1cs_reader.rs:54-249 -> (num_inputs, n_wires, constraints[(A, B, C)] with rows of (coeff, index))"""
+    assert data[:4] == b'r1cs' and struct.unpack_from('<I', data, 4)[0] == 1
+    nsec = struct.unpack_from('<I', data, 8)[0]
+    pos, off = 12, {}
+    for _ in range(nsec):
+        t, sz = struct.unpack_from('<IQ', data, pos); pos += 12
+        off[t] = pos; pos += sz
+    p = off[1]
+    assert struct.unpack_from('<I', data, p)[0] == 32 and int.from_bytes(data[p + 4:p + 36], 'little') == R_MOD
+    n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, n_cons = struct.unpack_from('<IIIIQI', data, p + 36)
+    p = off[2]
+    cons = []
+    for _ in range(n_cons):
+        trip = []
+        for _k in range(3):
+            n = struct.unpack_from('<I', data, p)[0]; p += 4
+            row = []
+            for _j in range(n):
+                wire = struct.unpack_from('<I', data, p)[0]
+                row.append((int.from_bytes(data[p + 4:p + 36], 'little'), wire)); p += 36
+            trip.append(row)
+        cons.append(tuple(trip))
+    return 1 + n_pub_in + n_pub_out, n_wires, cons

@@ -339,3 +339,68 @@ def test_gpu_setup_prove_verify_flow(ctx):
     assert o.verify(vk, w[1:circ.num_inputs], (p.a, p.b, p.c))
     assert not o.verify(vk, [(w[1] + 1) % o.R_MOD], (p.a, p.b, p.c))
     release(pk); release(cm)
+
+
+# ------------------------------------------------------------------------------------------------ LibsnarkReduction + R1CS route
+def _vk_from_pk(pk):
+    vk = o.ZKey()
+    def g1(a): return o._g1_from(np.ascontiguousarray(a).tobytes())
+    def g2(a): return o._g2_from(np.ascontiguousarray(a).tobytes())
+    vk.alpha_g1, vk.beta_g2, vk.gamma_g2, vk.delta_g2 = g1(pk.alpha_g1), g2(pk.beta_g2), g2(pk.gamma_g2), g2(pk.delta_g2)
+    vk.ic = [g1(x) for x in pk.gamma_abc_g1]
+    return vk
+
+
+@pytest.mark.parametrize('log_n', [3, 9, 11, 14])
+def test_libsnark_witness_map_vs_oracle(ctx, log_n):
+    from circom_compat_b200 import LibsnarkReduction, fr_to_mont, synth, release
+    circ, w = synth.circomlike_circuit(log_n)
+    cm = circ.matrices(with_c=True)
+    wm = fr_to_mont(w)
+    h = LibsnarkReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    ref = c.witness_map_libsnark(cm.num_constraints, cm.num_instance_variables, cm.a, cm.b, cm.c, wm)
+    assert np.array_equal(h, ref)
+    assert not h[-1].any()                                     # deg h <= n - 2
+    release(cm)
+
+
+def test_r1cs_route_setup_prove_verify(ctx):
+    """/root/reference/tests/groth16.rs:11-41 (mycircuit) and :75-105 (circuit2) with their real circom fixtures:
+    R1CS file -> matrices, snarkjs witness, Groth16<Bn254> = LibsnarkReduction setup -> prove -> verify; :42-74 negative."""
+    from circom_compat_b200 import R1CSFile, R1CS, read_wtns, Groth16, LibsnarkReduction, fr_to_mont, fr_from_mont, release
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = random.Random(99)
+    for r1cs_name, witness in (('mycircuit.r1cs', [1, 33, 3, 11]), ('circuit2.r1cs', None)):
+        r = R1CS.from_file(R1CSFile.new(open(os.path.join(root, 'tests', 'golden', r1cs_name), 'rb').read()))
+        w = witness or read_wtns(open(os.path.join(root, 'tests', 'golden', 'circuit2_witness.wtns'), 'rb').read())
+        circ = r.to_circuit()
+        cm = circ.matrices(with_c=True)
+        pk = Groth16.generate_random_parameters_with_reduction(circ, rng, ctx, LibsnarkReduction)
+        assert len(pk.h_query) == circ.domain_size - 1
+        wm = fr_to_mont(w)
+        p = Groth16.prove(pk, cm, wm, rng, ctx, LibsnarkReduction)
+        vk = _vk_from_pk(pk)
+        assert o.verify(vk, w[1:r.num_inputs], (p.a, p.b, p.c)), r1cs_name
+        assert not o.verify(vk, [(w[1] + 1) % o.R_MOD], (p.a, p.b, p.c))
+        # the witness map behind it is the oracle's
+        h = LibsnarkReduction.witness_map_from_matrices(cm, r.num_inputs, len(r.constraints), wm, ctx)
+        ni, nw, cons = r.num_inputs, r.num_variables, [tuple([(v, i) for i, v in lc] for lc in con) for con in r.constraints]
+        href = o.libsnark_witness_map_from_matrices([c_[0] for c_ in cons], [c_[1] for c_ in cons], [c_[2] for c_ in cons], ni, len(cons), w)
+        assert fr_from_mont(h) == href
+        release(pk); release(cm)
+
+
+def test_libsnark_proof_matches_cpu_oracle_bytes(ctx):
+    # same key, witness, r, s: GPU proof bytes == CPU oracle (libsnark h fed to the shared proof assembly)
+    from circom_compat_b200 import Groth16, LibsnarkReduction, fr_to_mont, synth, release
+    circ, w = synth.circomlike_circuit(12)
+    pk, td = synth.setup(ctx, circ, flavour='libsnark')
+    cm = circ.matrices(with_c=True)
+    wm = fr_to_mont(w)
+    r, s = 0x1234567, 0x7654321
+    p = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, circ.num_inputs, circ.num_constraints, wm, ctx, LibsnarkReduction)
+    href = c.fr_from_mont(c.witness_map_libsnark(cm.num_constraints, cm.num_instance_variables, cm.a, cm.b, cm.c, wm))
+    hi = c.limbs_to_ints(href)
+    da, db, dc = synth.expected_proof_dlogs(td, w, hi[:len(td.h_t)], r, s, circ.num_inputs)
+    assert o.G1.mul(o.G1_GEN, da) == p.a and o.G2.mul(o.G2_GEN, db) == p.b and o.G1.mul(o.G1_GEN, dc) == p.c
+    release(pk); release(cm)

@@ -161,3 +161,72 @@ def test_proof_formats(golden, test_zkey_bytes):
     assert t[0] == z.alpha_g1 and t[1] == ([z.beta_g2[0][1], z.beta_g2[0][0]], [z.beta_g2[1][1], z.beta_g2[1][0]])
     assert t[4] == [tuple(pt) for pt in z.ic]
     assert eth.inputs([33]) == [33]
+
+
+# ------------------------------------------------------------------------------------------------ R1CS route (host readers)
+R1CS_SAMPLE_HEX = """72316373 01000000 03000000 01000000 40000000 00000000 20000000
+ 010000f0 93f5e143 9170b979 48e83328 5d588181 b64550b8 29a031e1 724e6430 07000000 01000000 02000000 03000000 e8030000 00000000 03000000
+ 02000000 88020000 00000000
+ 02000000 05000000 03000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 06000000 08000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 03000000 00000000 02000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 02000000 14000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 03000000 0C000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 02000000 00000000 05000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 02000000 07000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 03000000 01000000 04000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 04000000 08000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 05000000 03000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 02000000 03000000 2C000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 06000000 06000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 00000000
+ 01000000 06000000 04000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 03000000 00000000 06000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 02000000 0B000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 03000000 05000000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 01000000 06000000 58020000 00000000 00000000 00000000 00000000 00000000 00000000 00000000
+ 03000000 38000000 00000000
+ 00000000 00000000 03000000 00000000 0a000000 00000000 0b000000 00000000 0c000000 00000000 0f000000 00000000 44010000 00000000"""
+
+
+def test_r1cs_reader_reference_sample():
+    # the iden3-spec sample and the assertions of /root/reference/src/circom/r1cs_reader.rs:257-338
+    from circom_compat_b200 import R1CSFile
+    f = R1CSFile.new(bytes.fromhex(R1CS_SAMPLE_HEX.replace('\n', '').replace(' ', '')))
+    h = f.header
+    assert (f.version, h.field_size, h.n_wires, h.n_pub_out, h.n_pub_in, h.n_prv_in, h.n_labels, h.n_constraints) == (1, 32, 7, 1, 2, 3, 0x03e8, 3)
+    assert len(f.constraints) == 3 and len(f.constraints[0][0]) == 2
+    assert f.constraints[0][0][0] == (5, 3) and f.constraints[2][1][0] == (0, 6) and len(f.constraints[1][2]) == 0
+    assert len(f.wire_mapping) == 7 and f.wire_mapping[1] == 3
+
+
+def test_r1cs_and_wtns_fixtures():
+    from circom_compat_b200 import R1CSFile, R1CS, read_wtns
+    from circom_compat_b200.r1cs import SerializationError
+    data = open(os.path.join(ROOT, 'tests', 'golden', 'circuit2.r1cs'), 'rb').read()
+    r = R1CS.from_file(R1CSFile.new(data))
+    ni, nw, cons = o.read_r1cs(data)
+    assert (r.num_inputs, r.num_variables, len(r.constraints)) == (ni, nw, len(cons)) == (2, 132, 131)
+    assert all([(v, w) for w, v in mine[k]] == ref[k] for mine, ref in zip(r.constraints, cons) for k in range(3))
+    w = read_wtns(open(os.path.join(ROOT, 'tests', 'golden', 'circuit2_witness.wtns'), 'rb').read())
+    assert len(w) == 132 and w[:4] == [1, 33, 3, 11]
+    assert all((sum(v * w[i] for i, v in c_[0]) * sum(v * w[i] for i, v in c_[1]) - sum(v * w[i] for i, v in c_[2])) % o.R_MOD == 0 for c_ in r.constraints)
+    with pytest.raises(SerializationError):
+        R1CSFile.new(b'zkey' + data[4:])
+    circ = r.to_circuit()
+    cm = circ.matrices(with_c=True)
+    assert cm.c is not None and cm.num_constraints == 131 and cm.num_instance_variables == 2
+
+
+def test_libsnark_oracles_agree_and_satisfy_qap_identity():
+    from circom_compat_b200 import R1CSFile, R1CS, read_wtns, fr_to_mont
+    data = open(os.path.join(ROOT, 'tests', 'golden', 'circuit2.r1cs'), 'rb').read()
+    r = R1CS.from_file(R1CSFile.new(data))
+    w = read_wtns(open(os.path.join(ROOT, 'tests', 'golden', 'circuit2_witness.wtns'), 'rb').read())
+    ni, nw, cons = o.read_r1cs(data)
+    A = [c_[0] for c_ in cons]; B = [c_[1] for c_ in cons]; Cm = [c_[2] for c_ in cons]
+    h = o.libsnark_witness_map_from_matrices(A, B, Cm, ni, len(cons), w)
+    assert len(h) == 256 and h[-1] == 0
+    cm = r.to_circuit().matrices(with_c=True)
+    hc = c.witness_map_libsnark(cm.num_constraints, cm.num_instance_variables, cm.a, cm.b, cm.c, fr_to_mont(w))
+    assert c.limbs_to_ints(c.fr_from_mont(hc)) == h
