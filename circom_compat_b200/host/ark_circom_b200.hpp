@@ -283,12 +283,14 @@ public:
         return pks_[&k] = h;
     }
 
-    b2g_mat* mat(const ConstraintMatrices& m, size_t n_vars) {
-        auto it = mats_.find(&m);
+    b2g_mat* mat(const ConstraintMatrices& m, size_t n_vars, uint32_t reduction = B2G_REDUCTION_CIRCOM) {
+        auto key = std::make_pair(&m, reduction);
+        auto it = mats_.find(key);
         if (it != mats_.end()) return it->second;
-        std::vector<uint32_t> rp[2], col[2]; std::vector<Fr> val[2];
-        const Matrix* src[2] = {&m.a, &m.b};
-        for (int k = 0; k < 2; k++) {
+        std::vector<uint32_t> rp[3], col[3]; std::vector<Fr> val[3];
+        const Matrix* src[3] = {&m.a, &m.b, &m.c};
+        const int nmat = reduction == B2G_REDUCTION_LIBSNARK ? 3 : 2;
+        for (int k = 0; k < nmat; k++) {
             rp[k].assign(m.num_constraints + 1, 0);
             for (size_t i = 0; i < m.num_constraints; i++) {
                 const auto& row = i < src[k]->size() ? (*src[k])[i] : Matrix::value_type();
@@ -298,19 +300,23 @@ public:
         }
         b2g_mat_desc d; memset(&d, 0, sizeof d);
         d.num_constraints = (uint32_t)m.num_constraints; d.num_inputs = (uint32_t)m.num_instance_variables; d.n_vars = (uint32_t)n_vars;
+        d.reduction = reduction;
         d.a_rowptr = rp[0].data(); d.a_col = col[0].data(); d.a_val = val[0].data();
         d.b_rowptr = rp[1].data(); d.b_col = col[1].data(); d.b_val = val[1].data();
+        if (nmat == 3) { d.c_rowptr = rp[2].data(); d.c_col = col[2].data(); d.c_val = val[2].data(); }
         b2g_mat* h = nullptr; check(b2g_matrices_load(ctx_, &d, &h));
-        return mats_[&m] = h;
+        return mats_[key] = h;
     }
 
 private:
     b2g_ctx* ctx_ = nullptr;
     std::map<const ProvingKey*, b2g_pk*> pks_;
-    std::map<const ConstraintMatrices*, b2g_mat*> mats_;
+    std::map<std::pair<const ConstraintMatrices*, uint32_t>, b2g_mat*> mats_;
 };
 
-struct CircomReduction {                                // src/circom/qap.rs:12-14
+template <uint32_t REDUCTION>
+struct Reduction {
+    static constexpr uint32_t ID = REDUCTION;
     static std::vector<Fr> witness_map_from_matrices(const ConstraintMatrices& matrices, size_t num_inputs, size_t num_constraints,
                                                      const std::vector<Fr>& full_assignment, Gpu& gpu = Gpu::instance()) {
         if (num_inputs != matrices.num_instance_variables || num_constraints != matrices.num_constraints)
@@ -319,12 +325,15 @@ struct CircomReduction {                                // src/circom/qap.rs:12-
         if (n > (size_t(1) << 27)) throw PolynomialDegreeTooLarge();
         std::vector<Fr> h(n);
         uint32_t dom = 0;
-        check(b2g_witness_map(gpu.ctx(), gpu.mat(matrices, full_assignment.size()), full_assignment.data(), h.data(), &dom));
+        check(b2g_witness_map(gpu.ctx(), gpu.mat(matrices, full_assignment.size(), REDUCTION), full_assignment.data(), h.data(), &dom));
         return h;
     }
 };
+typedef Reduction<B2G_REDUCTION_CIRCOM> CircomReduction;       // src/circom/qap.rs:12-14 (snarkjs keys)
+typedef Reduction<B2G_REDUCTION_LIBSNARK> LibsnarkReduction;   // ark-groth16's default QAP (tests/groth16.rs:9,25-35; needs matrices.c)
 
-struct Groth16 {                                        // Groth16::<Bn254, CircomReduction>
+template <class QAP = CircomReduction>
+struct Groth16T {                                       // Groth16::<Bn254, QAP>
     static Proof create_proof_with_reduction_and_matrices(const ProvingKey& pk, const Fr& r, const Fr& s, const ConstraintMatrices& matrices,
                                                           size_t num_inputs, size_t num_constraints, const std::vector<Fr>& full_assignment,
                                                           Gpu& gpu = Gpu::instance()) {
@@ -333,7 +342,7 @@ struct Groth16 {                                        // Groth16::<Bn254, Circ
         if (full_assignment.size() != pk.a_query.size()) throw SynthesisError("AssignmentMissing: full_assignment length != n_vars");
         BigInt256 rb = r.into_bigint(), sb = s.into_bigint();
         Proof p;
-        check(b2g_prove(gpu.ctx(), gpu.pk(pk), gpu.mat(matrices, full_assignment.size()), rb.l, sb.l, full_assignment.data(), p.bytes));
+        check(b2g_prove(gpu.ctx(), gpu.pk(pk), gpu.mat(matrices, full_assignment.size(), QAP::ID), rb.l, sb.l, full_assignment.data(), p.bytes));
         return p;
     }
 
@@ -343,6 +352,67 @@ struct Groth16 {                                        // Groth16::<Bn254, Circ
         Fr r = Fr::rand(rng), s = Fr::rand(rng);        // r first, then s (create_random_proof_with_reduction)
         return create_proof_with_reduction_and_matrices(pk, r, s, matrices, matrices.num_instance_variables, matrices.num_constraints,
                                                         full_assignment, gpu);
+    }
+};
+
+typedef Groth16T<CircomReduction> Groth16;
+
+// ---------------------------------------------------------------------------------------------- R1CS route (host)
+// R1CSFile / R1CS: /root/reference/src/circom/r1cs_reader.rs:54-249; to_matrices = what CircomCircuit::generate_constraints
+// + ConstraintSystem::to_matrices yield (src/circom/circuit.rs:30-82: column index = wire index).
+struct R1CS {
+    size_t num_inputs = 0, num_aux = 0, num_variables = 0;
+    struct Constraint { std::vector<std::pair<size_t, Fr>> a, b, c; };          // (index, coeff): src/circom/mod.rs:13-14
+    std::vector<Constraint> constraints;
+    std::vector<uint64_t> wire_mapping;
+
+    static R1CS read(std::istream& r) {
+        char magic[4]; detail::read_exact(r, magic, 4);
+        if (memcmp(magic, "r1cs", 4)) throw SerializationError("Invalid magic number");
+        if (detail::read_le<uint32_t>(r) != 1) throw SerializationError("Unsupported version");
+        uint32_t nsec = detail::read_le<uint32_t>(r);
+        std::map<uint32_t, std::pair<uint64_t, uint64_t>> sec;
+        for (uint32_t i = 0; i < nsec; i++) {
+            uint32_t t = detail::read_le<uint32_t>(r); uint64_t sz = detail::read_le<uint64_t>(r);
+            sec[t] = {(uint64_t)r.tellg(), sz};
+            r.seekg((std::streamoff)sz, std::ios::cur);
+        }
+        for (uint32_t t : {1u, 2u, 3u}) if (!sec.count(t)) throw SerializationError("missing r1cs section");
+        r.clear(); r.seekg((std::streamoff)sec[1].first);
+        if (detail::read_le<uint32_t>(r) != 32) throw SerializationError("This parser only supports 32-byte fields");
+        uint64_t prime[4]; detail::read_exact(r, prime, 32);
+        if (memcmp(prime, detail::FR_P, 32)) throw SerializationError("This parser only supports bn256");
+        uint32_t n_wires = detail::read_le<uint32_t>(r), n_pub_out = detail::read_le<uint32_t>(r), n_pub_in = detail::read_le<uint32_t>(r);
+        detail::read_le<uint32_t>(r); detail::read_le<uint64_t>(r);
+        uint32_t n_cons = detail::read_le<uint32_t>(r);
+        R1CS out;
+        out.num_inputs = 1 + n_pub_in + n_pub_out; out.num_variables = n_wires; out.num_aux = n_wires - out.num_inputs;
+        r.seekg((std::streamoff)sec[2].first);
+        auto lc = [&](std::vector<std::pair<size_t, Fr>>& v) {
+            uint32_t n = detail::read_le<uint32_t>(r);
+            for (uint32_t k = 0; k < n; k++) { uint32_t w = detail::read_le<uint32_t>(r); BigInt256 b; detail::read_exact(r, b.l, 32); v.push_back({w, Fr::from_bigint(b)}); }
+        };
+        out.constraints.resize(n_cons);
+        for (auto& c : out.constraints) { lc(c.a); lc(c.b); lc(c.c); }
+        if (sec[3].second != (uint64_t)n_wires * 8) throw SerializationError("Invalid map section size");
+        r.seekg((std::streamoff)sec[3].first);
+        out.wire_mapping.resize(n_wires);
+        if (n_wires) detail::read_exact(r, out.wire_mapping.data(), (size_t)n_wires * 8);
+        if (n_wires && out.wire_mapping[0] != 0) throw SerializationError("Wire 0 should always be mapped to 0");
+        return out;
+    }
+
+    ConstraintMatrices to_matrices() const {
+        ConstraintMatrices m;
+        m.num_instance_variables = num_inputs; m.num_witness_variables = num_aux; m.num_constraints = constraints.size();
+        m.a.resize(constraints.size()); m.b.resize(constraints.size()); m.c.resize(constraints.size());
+        for (size_t i = 0; i < constraints.size(); i++) {
+            for (auto& e : constraints[i].a) m.a[i].push_back({e.second, e.first});
+            for (auto& e : constraints[i].b) m.b[i].push_back({e.second, e.first});
+            for (auto& e : constraints[i].c) m.c[i].push_back({e.second, e.first});
+            m.a_num_non_zero += m.a[i].size(); m.b_num_non_zero += m.b[i].size(); m.c_num_non_zero += m.c[i].size();
+        }
+        return m;
     }
 };
 
