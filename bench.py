@@ -224,10 +224,17 @@ def run_ours(args):
         inflight = 1 if sharded else max(1, args.inflight)
         ctxs = [Context(local, rank if sharded else 0, world if sharded else 1) for _ in range(inflight)]
         groups = [None] * inflight
+        fused = sharded and args.exchange == 'p2p'
+        if fused:
+            sharding.connect_p2p(ctxs[0], dist)                    # CUDA-IPC handles of the exchange buffers, once
+            ctxs[0].prepare(pk, cm)
+            dist.barrier()
 
         def one_proof(i=0):
             if not sharded:
                 return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wms[i], ctxs[i])
+            if fused:
+                return Groth16.prove_sharded_p2p(pk, cm, R_FIX, S_FIX, wms[i], ctxs[i])
             return sharding.prove_sharded(ctxs[i], pk, cm, wms[i], R_FIX, S_FIX, dist, dev, groups[i])
 
         def run_steps(total):
@@ -325,7 +332,8 @@ def run_ours(args):
         o_ = measure(other_mode)
         assert o_["proof"].data == proof.data, "sharded and whole proofs differ"
         other = {"mode": other_mode, "value": o_["value"], "e2e_value": o_["e2e_value"], "unit": "proofs/s", "latency_ms": o_["latency_ms"],
-                 "scaling": "strong" if other_mode == 'sharded' else "weak", "gpu_launches": o_["launches"]}
+                 "scaling": "strong" if other_mode == 'sharded' else "weak", "gpu_launches": o_["launches"],
+                 "exchange": args.exchange if other_mode == 'sharded' else None}
         for c_ in o_["ctxs"]:
             c_.close()
 
@@ -347,7 +355,7 @@ def run_ours(args):
     if rank == 0:
         cfg = workload_config(args, circ)
         cfg["in_flight"] = 1 if main_mode == "sharded" else inflight
-        cfg["parallelism"] = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs + one NCCL all-gather of 768 B partials per proof"
+        cfg["parallelism"] = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs; 768 B partials exchanged " + ("inside the assembly kernels over NVLink peer memory" if args.exchange == 'p2p' else "with one NCCL all-gather")
                                                               if main_mode == 'sharded' else f"{world} replicas (one whole prover per GPU)")
         sharded = main_mode == 'sharded'
         value = main["value"]
@@ -390,6 +398,7 @@ def main():
     ap.add_argument('--log-n', type=int, default=20)
     ap.add_argument('--workload', default='chain', choices=['chain', 'circomlike'])
     ap.add_argument('--mode', default='replicas', choices=['sharded', 'replicas'], help='N>1: headline mode (the other one is measured too, see other_mode)')
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded mode: partials folded from NVLink peer memory inside the kernels (p2p) or gathered with one NCCL all-gather (nccl)')
     ap.add_argument('--one-mode', action='store_true', help='N>1: measure only --mode')
     ap.add_argument('--inflight', type=int, default=2, help='proofs in flight per GPU (one Context + host thread each)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')

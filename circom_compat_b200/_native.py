@@ -34,9 +34,9 @@ class MatDesc(C.Structure):
                [(k, C.c_void_p) for k in ('a_rowptr', 'a_col', 'a_val', 'b_rowptr', 'b_col', 'b_val', 'c_rowptr', 'c_col', 'c_val')]
 
 
-EXPORTS = ['b2g_last_error', 'b2g_version', 'b2g_device_count', 'b2g_ctx_create', 'b2g_ctx_destroy', 'b2g_pk_load', 'b2g_pk_free',
+EXPORTS = ['b2g_last_error', 'b2g_version', 'b2g_device_count', 'b2g_ctx_create', 'b2g_ctx_destroy', 'b2g_ctx_prepare', 'b2g_pk_load', 'b2g_pk_free',
            'b2g_matrices_load', 'b2g_matrices_free', 'b2g_witness_map', 'b2g_prove', 'b2g_prove_partial', 'b2g_prove_finish',
-           'b2g_msm_g1', 'b2g_msm_g2', 'b2g_ntt', 'b2g_fixed_base_g1', 'b2g_fixed_base_g2', 'b2g_test_op', 'b2g_last_timings',
+           'b2g_p2p_export', 'b2g_p2p_import', 'b2g_p2p_connect_local', 'b2g_prove_sharded_p2p', 'b2g_msm_g1', 'b2g_msm_g2', 'b2g_ntt', 'b2g_fixed_base_g1', 'b2g_fixed_base_g2', 'b2g_test_op', 'b2g_last_timings',
            'b2g_bench_device', 'b2g_bench_msm', 'b2g_launch_count']
 
 _lib = None
@@ -56,6 +56,7 @@ def lib():
         vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
         L.b2g_ctx_create.argtypes = [i, i, i, C.POINTER(vp)]
         L.b2g_ctx_destroy.argtypes = [vp]
+        L.b2g_ctx_prepare.argtypes = [vp, vp, vp]
         L.b2g_pk_load.argtypes = [vp, C.POINTER(PkDesc), C.POINTER(vp)]
         L.b2g_pk_free.argtypes = [vp]
         L.b2g_matrices_load.argtypes = [vp, C.POINTER(MatDesc), C.POINTER(vp)]
@@ -64,6 +65,10 @@ def lib():
         L.b2g_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_prove_partial.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_prove_finish.argtypes = [vp, vp, vp, i, vp, vp, vp]
+        L.b2g_p2p_export.argtypes = [vp, vp]
+        L.b2g_p2p_import.argtypes = [vp, vp, i]
+        L.b2g_p2p_connect_local.argtypes = [vp, i]
+        L.b2g_prove_sharded_p2p.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_msm_g1.argtypes = [vp, vp, vp, sz, i, vp]
         L.b2g_msm_g2.argtypes = [vp, vp, vp, sz, i, vp]
         L.b2g_ntt.argtypes = [vp, vp, i, i]

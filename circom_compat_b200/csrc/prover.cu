@@ -47,6 +47,12 @@ struct b2g_ctx {
     size_t cap_w = 0, cap_n = 0;
     float last_ms[16] = {};
     bool pre_valid = false; uint32_t pre_r[8] = {}, pre_s[8] = {};   // (r, s) whose glue_pre result sits in d_pre
+    // peer-memory exchange (b2g_prove_sharded_p2p): own buffer + every rank's buffer as seen from this device
+    uint8_t* d_xchg = nullptr;                 // XCHG_BYTES: 2 slots x {epoch u64 @0, partial @256}
+    uint8_t** d_peer_ptrs = nullptr;           // device array [shard_count]
+    void* peer_mapped[64] = {};                // cudaIpcOpenMemHandle results (to close)
+    int peers_imported = 0;
+    unsigned long long epoch = 0;
 };
 
 struct b2g_pk {
@@ -149,6 +155,60 @@ __global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count
         }
         G1::Aff c = G1::to_affine(acc);
         store_canon(proof, 6, c.x); store_canon(proof, 7, c.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ peer-memory exchange
+constexpr size_t XCHG_SLOT = 1280;                    // epoch word at +0, 768-byte partial at +256, padded
+constexpr size_t XCHG_BYTES = 2 * XCHG_SLOT;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// copy this rank's partial into its exchange slot and release the epoch (visible to peers over NVLink)
+__global__ void xchg_publish_kernel(const uint8_t* __restrict__ partial, uint8_t* __restrict__ xchg, unsigned long long epoch) {
+    uint8_t* slot = xchg + (epoch & 1ull) * XCHG_SLOT;
+    const uint4* src = reinterpret_cast<const uint4*>(partial);
+    uint4* dst = reinterpret_cast<uint4*>(slot + 256);
+    if (threadIdx.x < B2G_PARTIAL_BYTES / 16) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long*>(slot), epoch);
+}
+
+// wait until every rank has published `epoch`, then gather the partials from peer memory (rank order) into `gathered`
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// The wait is bounded (a peer that never publishes must not wedge the GPU): after timeout_ns the rank's slot of
+// `timed_out` is set and the host reports B2G_E_DEVICE.
+__global__ void xchg_gather_kernel(uint8_t* const* __restrict__ peers, int count, unsigned long long epoch, uint8_t* __restrict__ gathered,
+                                   unsigned long long timeout_ns, unsigned int* __restrict__ timed_out) {
+    const int k = blockIdx.x;                         // one CTA per rank
+    const uint8_t* slot = peers[k] + (epoch & 1ull) * XCHG_SLOT;
+    if (threadIdx.x == 0) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(slot);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) < epoch) {
+            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(timed_out, 1u + (unsigned)k); break; }
+            __nanosleep(500);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < B2G_PARTIAL_BYTES / 16) {
+        const uint4* src = reinterpret_cast<const uint4*>(slot + 256);
+        uint4 v;
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + threadIdx.x) : "memory");
+        reinterpret_cast<uint4*>(gathered + (size_t)k * B2G_PARTIAL_BYTES)[threadIdx.x] = v;
     }
 }
 
@@ -401,6 +461,9 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         CUDA_CHECK(cudaMalloc(&ctx->d_partials_all, 64 * B2G_PARTIAL_BYTES));
         CUDA_CHECK(cudaMalloc(&ctx->d_proof, 256));
         CUDA_CHECK(cudaMalloc(&ctx->d_pre, 3 * 128 + 256));
+        CUDA_CHECK(cudaMalloc(&ctx->d_xchg, XCHG_BYTES + 256));            // plain cudaMalloc: exportable through CUDA IPC
+        CUDA_CHECK(cudaMemset(ctx->d_xchg, 0, XCHG_BYTES + 256));
+        CUDA_CHECK(cudaMalloc(&ctx->d_peer_ptrs, 64 * sizeof(uint8_t*)));
         msm_init_kernels();
         *out = ctx;
     });
@@ -414,7 +477,8 @@ int b2g_ctx_destroy(b2g_ctx* ctx) {
         for (int i = 0; i < NQ; i++) { if (ctx->scratch_ok) msm_scratch_free(ctx->scratch[i]); cudaStreamDestroy(ctx->st[i]); cudaEventDestroy(ctx->ev_done[i]); }
         cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_post); cudaStreamDestroy(ctx->st_glue);
         for (auto& e : ctx->ev_t) cudaEventDestroy(e);
-        for (void* p : {(void*)ctx->d_partial, (void*)ctx->d_partials_all, (void*)ctx->d_proof, (void*)ctx->d_pre, (void*)ctx->d_w,
+        for (int k = 0; k < 64; k++) if (ctx->peer_mapped[k]) cudaIpcCloseMemHandle(ctx->peer_mapped[k]);
+        for (void* p : {(void*)ctx->d_xchg, (void*)ctx->d_peer_ptrs, (void*)ctx->d_partial, (void*)ctx->d_partials_all, (void*)ctx->d_proof, (void*)ctx->d_pre, (void*)ctx->d_w,
                         (void*)ctx->d_a, (void*)ctx->d_b, (void*)ctx->d_c, (void*)ctx->d_h}) if (p) cudaFree(p);
         delete ctx;
     });
@@ -605,6 +669,97 @@ int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int cou
         launch_glue_post(ctx, pk, ctx->d_partials_all, count, r_canon, s_canon, s0);
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
+    });
+}
+
+int b2g_ctx_prepare(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
+    return guarded([&] {
+        check_shapes(ctx, pk, mat);
+        DevGuard g(ctx->device);
+        ensure_witness_buffers(ctx, mat->n_vars, mat->n);
+        ensure_scratch(ctx, pk);
+        CUDA_CHECK(cudaDeviceSynchronize());
+    });
+}
+
+int b2g_p2p_export(b2g_ctx* ctx, void* handle_out) {
+    return guarded([&] {
+        if (!ctx || !handle_out) throw_error(B2G_E_SHAPE, "null pointer");
+        static_assert(sizeof(cudaIpcMemHandle_t) == B2G_IPC_HANDLE_BYTES, "IPC handle size");
+        DevGuard g(ctx->device);
+        cudaIpcMemHandle_t h;
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, ctx->d_xchg));
+        memcpy(handle_out, &h, sizeof h);
+    });
+}
+
+int b2g_p2p_import(b2g_ctx* ctx, const void* handles_all, int count) {
+    return guarded([&] {
+        if (!ctx || !handles_all) throw_error(B2G_E_SHAPE, "null pointer");
+        if (count != ctx->shard_count) throw_error(B2G_E_SHAPE, "need one handle per shard rank");
+        DevGuard g(ctx->device);
+        std::vector<uint8_t*> ptrs((size_t)count, nullptr);
+        for (int k = 0; k < count; k++) {
+            if (k == ctx->shard_rank) { ptrs[k] = ctx->d_xchg; continue; }
+            cudaIpcMemHandle_t h; memcpy(&h, (const uint8_t*)handles_all + (size_t)k * sizeof h, sizeof h);
+            void* p = nullptr;
+            CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->peer_mapped[k] = p; ptrs[k] = (uint8_t*)p;
+        }
+        CUDA_CHECK(cudaMemcpy(ctx->d_peer_ptrs, ptrs.data(), (size_t)count * sizeof(uint8_t*), cudaMemcpyHostToDevice));
+        ctx->peers_imported = count;
+    });
+}
+
+static unsigned long long p2p_timeout_ns() {
+    const char* v = getenv("B2G_P2P_TIMEOUT_MS");
+    long ms = v && *v ? strtol(v, nullptr, 10) : 20000;
+    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+}
+
+int b2g_p2p_connect_local(b2g_ctx** ctxs, int count) {
+    return guarded([&] {
+        if (!ctxs || count < 1 || count > 64) throw_error(B2G_E_SHAPE, "bad arguments");
+        for (int k = 0; k < count; k++) if (!ctxs[k] || ctxs[k]->shard_rank != k || ctxs[k]->shard_count != count) throw_error(B2G_E_SHAPE, "contexts must be the shard ranks 0..count-1 in order");
+        std::vector<uint8_t*> ptrs((size_t)count);
+        for (int k = 0; k < count; k++) ptrs[k] = ctxs[k]->d_xchg;
+        for (int k = 0; k < count; k++) {
+            DevGuard g(ctxs[k]->device);
+            for (int j = 0; j < count; j++) if (ctxs[j]->device != ctxs[k]->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+                cudaGetLastError();
+            }
+            CUDA_CHECK(cudaMemcpy(ctxs[k]->d_peer_ptrs, ptrs.data(), (size_t)count * sizeof(uint8_t*), cudaMemcpyHostToDevice));
+            ctxs[k]->peers_imported = count;
+        }
+    });
+}
+
+int b2g_prove_sharded_p2p(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, uint8_t proof_out[256]) {
+    return guarded([&] {
+        if (!ctx || !pk || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
+        if (ctx->peers_imported != ctx->shard_count) throw_error(B2G_E_SHAPE, "b2g_p2p_import has not been called with every rank's handle");
+        DevGuard g(ctx->device);
+        launch_glue_pre(ctx, pk, r_canon, s_canon);
+        prove_common(ctx, pk, mat, w_mont);
+        cudaStream_t s0 = ctx->st[0];
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
+        const unsigned long long epoch = ++ctx->epoch;
+        xchg_publish_kernel<<<1, 64, 0, s0>>>(ctx->d_partial, ctx->d_xchg, epoch);
+        unsigned int* d_flag = reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES);       // local word after the two slots
+        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 4, s0));
+        xchg_gather_kernel<<<ctx->shard_count, 64, 0, s0>>>(ctx->d_peer_ptrs, ctx->shard_count, epoch, ctx->d_partials_all,
+                                                            p2p_timeout_ns(), d_flag);
+        g_launch_count += 2;
+        launch_glue_post(ctx, pk, ctx->d_partials_all, ctx->shard_count, r_canon, s_canon, s0);
+        unsigned int flag = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s0));
+        CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
+        CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+        if (flag) throw_error(B2G_E_DEVICE, "peer exchange timed out waiting for shard rank " + std::to_string(flag - 1));
+        collect_timings(ctx);
     });
 }
 

@@ -98,6 +98,19 @@ class Context:
             _MAT_HANDLES[key] = (h, m)
         return _MAT_HANDLES[key][0]
 
+    def prepare(self, pk: ProvingKey, matrices: ConstraintMatrices, reduction_id: int = N.REDUCTION_CIRCOM) -> None:
+        """load (pk, matrices) and allocate this context's scratch now instead of inside the first proof"""
+        N.check(N.lib().b2g_ctx_prepare(self._h, self.pk_handle(pk), self.mat_handle(matrices, pk.n_vars, reduction_id)))
+
+    def p2p_export(self) -> bytes:
+        buf = np.zeros(64, dtype=np.uint8)
+        N.check(N.lib().b2g_p2p_export(self._h, _ptr(buf)))
+        return buf.tobytes()
+
+    def p2p_import(self, handles) -> None:
+        blob = np.frombuffer(b''.join(handles), dtype=np.uint8).copy()
+        N.check(N.lib().b2g_p2p_import(self._h, _ptr(blob), len(handles)))
+
     def last_timings(self) -> dict:
         buf = (C.c_float * 16)()
         N.check(N.lib().b2g_last_timings(self._h, buf))
@@ -281,6 +294,16 @@ class Groth16:
         ss = _scalar_bytes(s) if s is not None else None
         N.check(N.lib().b2g_prove_partial(ctx._h, ph, mh, _ptr(rr) if rr is not None else None, _ptr(ss) if ss is not None else None, _ptr(w), _ptr(out)))
         return out
+
+    @staticmethod
+    def prove_sharded_p2p(pk: ProvingKey, matrices: ConstraintMatrices, r, s, full_assignment, ctx: Context, reduction=CircomReduction) -> Proof:
+        """Sharded proof whose exchange runs inside the kernels over NVLink peer memory (sharding.connect_p2p first)."""
+        w = _c(full_assignment)
+        ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars, reduction.ID)
+        rr, ss = _scalar_bytes(r), _scalar_bytes(s)
+        out = np.zeros(256, dtype=np.uint8)
+        N.check(N.lib().b2g_prove_sharded_p2p(ctx._h, ph, mh, _ptr(rr), _ptr(ss), _ptr(w), _ptr(out)))
+        return Proof(out.tobytes())
 
     @staticmethod
     def prove_finish(pk: ProvingKey, partials: np.ndarray, r, s, ctx: Context) -> Proof:

@@ -42,3 +42,21 @@ def prove_sharded(ctx, pk, matrices, w_mont, r, s, dist, device=None, group=None
     part = Groth16.prove_partial(pk, matrices, w_mont, ctx, r, s)
     allp = all_gather_partials(part, dist, device, group)
     return Groth16.prove_finish(pk, allp, r, s, ctx)
+
+
+def connect_p2p(ctx, dist, group=None) -> None:
+    """Exchange the CUDA-IPC handles of every rank's exchange buffer (host-side, once) so that Groth16.prove_sharded_p2p
+    can fold the partials straight out of NVLink peer memory."""
+    handles = [None] * dist.get_world_size()
+    dist.all_gather_object(handles, ctx.p2p_export(), group=group)
+    ctx.p2p_import(handles)
+
+
+def connect_p2p_local(ctxs) -> None:
+    """Same wiring for shard contexts living in one process, ONE CONTEXT PER GPU.  (Several shard contexts on the same
+    device of one process can alias the same hardware work queue, where a rank waiting for its peer blocks that peer's
+    kernels; separate processes - the deployment model, one per GPU - do not share queues.)"""
+    import ctypes as C
+    from . import _native as N
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    N.check(N.lib().b2g_p2p_connect_local(arr, len(ctxs)))

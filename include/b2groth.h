@@ -103,6 +103,10 @@ B2G_API int b2g_device_count(int* count);
 B2G_API int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out);
 B2G_API int b2g_ctx_destroy(b2g_ctx* ctx);
 
+/* Optional: allocate this context's per-proof scratch for (pk, mat) now (otherwise the first proof does it, which
+ * synchronises the device - do it up front when several contexts share a device). */
+B2G_API int b2g_ctx_prepare(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat);
+
 B2G_API int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* desc, b2g_pk** out);
 B2G_API int b2g_pk_free(b2g_pk* pk);
 B2G_API int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* desc, b2g_mat** out);
@@ -126,6 +130,21 @@ B2G_API int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void
                               void* partial_out);
 B2G_API int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int count, const void* r_canon,
                      const void* s_canon, uint8_t proof_out[256]);
+
+/* Sharded proof with the exchange fused into the proof-assembly kernel (NVLink peer memory instead of a host-driven
+ * collective).  Every rank owns an exchange buffer in its HBM (two slots of 768 B + an epoch word each); peers map it
+ * through CUDA IPC.  b2g_prove_sharded_p2p runs the partial MSMs, publishes the partial with a system-scope release of
+ * the epoch, and the assembly kernel acquires every peer's epoch and folds the partials straight out of peer memory in
+ * rank order.  All ranks must call it for the same proof; every rank obtains identical bytes.
+ *   b2g_p2p_export  : 64-byte cudaIpcMemHandle_t of this context's exchange buffer
+ *   b2g_p2p_import  : handles of ALL ranks in rank order (count x 64 bytes; the own entry is ignored) */
+#define B2G_IPC_HANDLE_BYTES 64
+B2G_API int b2g_p2p_export(b2g_ctx* ctx, void* handle_out);
+B2G_API int b2g_p2p_import(b2g_ctx* ctx, const void* handles_all, int count);
+/* same wiring for shard contexts that live in ONE process (IPC handles cannot be opened by their exporter): ctxs in rank order */
+B2G_API int b2g_p2p_connect_local(b2g_ctx** ctxs, int count);
+B2G_API int b2g_prove_sharded_p2p(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon,
+                                  const void* w_mont, uint8_t proof_out[256]);
 
 /* Kernel-level entry points (parity tests, benchmarks). All pointers host. */
 B2G_API int b2g_msm_g1(b2g_ctx* ctx, const void* bases, const void* scalars, size_t n, int scalars_mont, void* out_xy_mont);
