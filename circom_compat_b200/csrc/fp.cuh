@@ -162,10 +162,11 @@ struct Fp {
     // ------------------------------------------------------------------ Montgomery product
     // acc[0..7] = { lo,hi of x0*b ; x1*b ; x2*b ; x3*b }
     static __device__ __forceinline__ void mul4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
-        asm("mul.lo.u32 %0, %8, %12;\n\t mul.hi.u32 %1, %8, %12;\n\t"
-            "mul.lo.u32 %2, %9, %12;\n\t mul.hi.u32 %3, %9, %12;\n\t"
-            "mul.lo.u32 %4, %10, %12;\n\t mul.hi.u32 %5, %10, %12;\n\t"
-            "mul.lo.u32 %6, %11, %12;\n\t mul.hi.u32 %7, %11, %12;"
+        // mul.wide.u32 is ONE IMAD.WIDE; a mul.lo/mul.hi pair without a carry chain is left unfused by ptxas (IMAD + IMAD.HI)
+        asm("{\n\t.reg .u64 t0, t1, t2, t3;\n\t"
+            "mul.wide.u32 t0, %8, %12;\n\t mul.wide.u32 t1, %9, %12;\n\t"
+            "mul.wide.u32 t2, %10, %12;\n\t mul.wide.u32 t3, %11, %12;\n\t"
+            "mov.b64 {%0, %1}, t0;\n\t mov.b64 {%2, %3}, t1;\n\t mov.b64 {%4, %5}, t2;\n\t mov.b64 {%6, %7}, t3;\n\t}"
             : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7])
             : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
     }
@@ -184,7 +185,7 @@ struct Fp {
         asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
             "madc.lo.cc.u32 %2, %9, %12, %2;\n\t madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
             "madc.lo.cc.u32 %4, %10, %12, %4;\n\t madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
-            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t madc.hi.u32 %7, %11, %12, %7;"
+            "madc.lo.cc.u32 %6, %11, %12, %6;\n\t madc.hi.cc.u32 %7, %11, %12, %7;"
             : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
             : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
     }
@@ -194,7 +195,7 @@ struct Fp {
             "madc.lo.cc.u32 %0, %9, %13, %2;\n\t madc.hi.cc.u32 %1, %9, %13, %3;\n\t"
             "madc.lo.cc.u32 %2, %10, %13, %4;\n\t madc.hi.cc.u32 %3, %10, %13, %5;\n\t"
             "madc.lo.cc.u32 %4, %11, %13, %6;\n\t madc.hi.cc.u32 %5, %11, %13, %7;\n\t"
-            "madc.lo.cc.u32 %6, %12, %13, 0;\n\t madc.hi.u32 %7, %12, %13, 0;"
+            "madc.lo.cc.u32 %6, %12, %13, 0;\n\t madc.hi.cc.u32 %7, %12, %13, 0;"
             : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(x0)
             : "r"(a1), "r"(a3), "r"(a5), "r"(a7), "r"(b));
     }

@@ -7,11 +7,13 @@
 //   * the bases never change between proofs, and HBM is 180 GB, so at key-load time every base P_i is expanded into the
 //     affine table T[w][i] = 2^(c*w) * P_i (w = 0..nwin-1).  All windows then share ONE bucket set of 2^(c-1) buckets:
 //     no per-window bucket reduction and no Horner doubling chain on the critical path.
-//   * per proof: (1) digit histogram, (2) exclusive scan, (3) scatter of (table row | sign) into bucket-sorted order
-//     - a counting sort with atomics, no library sort; (4) perfectly load-balanced accumulation: each thread owns a
-//     fixed-length run of the sorted list, mixed-adds its gathered bases in registers (XYZZ), and emits complete
-//     buckets directly and at most two boundary fragments; (5) fragments are folded per bucket (big buckets by a whole
-//     CTA); (6) the weighted bucket sum sum_b (b+1)*B_b by chunked running sums + a shared-memory tree.
+//   * per proof: (1) canonical scalars + digit histogram (one thread per (window, scalar)), (2) exclusive scan,
+//     (3) scatter of (table row | sign) into bucket-sorted order - a counting sort with warp-aggregated atomics, no
+//     library sort; the sorted list is shared by every query that pairs the same scalars (L, A, B1, B2);
+//     (4) perfectly load-balanced accumulation: each thread owns a fixed-length run of the sorted list, mixed-adds its
+//     gathered bases in registers (XYZZ), and emits complete buckets directly and at most two boundary fragments;
+//     (5) fragments are folded per bucket (big buckets by a whole CTA); (6) the weighted bucket sum sum_b (b+1)*B_b by
+//     chunked running sums, a small double-and-add and a shared-memory tree.
 //   Nothing in (1)-(6) synchronises with the host.
 #pragma once
 #include "ec.cuh"
@@ -49,15 +51,5 @@ inline int msm_pick_c(uint32_t n) {
     return c;
 }
 inline int msm_nwin(int c) { return (255 + c - 1) / c; }
-
-// signed digit of window w given the running carry (ark-ec make_digits)
-__device__ __forceinline__ int32_t msm_digit(const uint32_t* k, int c, int w, uint32_t& carry) {
-    uint32_t off = (uint32_t)w * (uint32_t)c, limb = off >> 5, sh = off & 31u;
-    uint64_t v = limb < 8 ? (uint64_t)k[limb] : 0ull;
-    if (limb + 1 < 8) v |= (uint64_t)k[limb + 1] << 32;
-    uint32_t coef = ((uint32_t)(v >> sh) & ((1u << c) - 1u)) + carry;
-    carry = (coef + (1u << (c - 1))) >> c;
-    return (int32_t)coef - (int32_t)(carry << c);
-}
 
 }  // namespace b2g

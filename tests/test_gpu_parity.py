@@ -246,8 +246,22 @@ def test_error_behaviour(ctx, test_zkey_bytes):
     pk, cm = read_zkey(test_zkey_bytes)
     with pytest.raises(ValueError):
         Groth16.create_proof_with_reduction_and_matrices(pk, 1, 1, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont([1, 2, 3]), ctx)
+    with pytest.raises(B2gError) as e:
+        ctx.test_op(99, np.zeros((1, 4), dtype=np.uint64))            # unknown op: B2G_E_SHAPE, nothing launched
+    assert e.value.code == -2
+    # a sharded context refuses the whole-proof entry point, a whole context refuses foreign shards' keys
+    from circom_compat_b200 import Context
+    cx = Context(0, 0, 2)
     with pytest.raises(B2gError):
-        ctx.ntt(np.zeros((1 << 3, 4), dtype=np.uint64)[:0].reshape(0, 4)) if False else ctx.test_op(99, np.zeros((1, 4), dtype=np.uint64))
+        Groth16.create_proof_with_reduction_and_matrices(pk, 1, 1, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont([1, 33, 3, 11]), cx)
+    cx.close()
+    # domain limit: next_pow2(num_constraints + num_inputs) must leave room for the doubled domain (qap.rs:31,63-66)
+    from circom_compat_b200 import PolynomialDegreeTooLarge, ConstraintMatrices
+    import numpy as _np
+    huge = ConstraintMatrices(2, 2, (1 << 27) + 1, 0, 0, 0, (_np.zeros((1 << 27) + 2, dtype=_np.uint32), _np.zeros(0, dtype=_np.uint32), _np.zeros((0, 4), dtype=_np.uint64)),
+                              (_np.zeros((1 << 27) + 2, dtype=_np.uint32), _np.zeros(0, dtype=_np.uint32), _np.zeros((0, 4), dtype=_np.uint64)))
+    with pytest.raises(PolynomialDegreeTooLarge):
+        ctx.mat_handle(huge, 4)
 
 
 def test_cpp_host_mirror_proves_golden(golden, tmp_path):
