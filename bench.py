@@ -400,7 +400,7 @@ def main():
     ap.add_argument('--mode', default='replicas', choices=['sharded', 'replicas'], help='N>1: headline mode (the other one is measured too, see other_mode)')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded mode: partials folded from NVLink peer memory inside the kernels (p2p) or gathered with one NCCL all-gather (nccl)')
     ap.add_argument('--one-mode', action='store_true', help='N>1: measure only --mode')
-    ap.add_argument('--inflight', type=int, default=2, help='proofs in flight per GPU (one Context + host thread each)')
+    ap.add_argument('--inflight', type=int, default=3, help='proofs in flight per GPU (one Context + host thread each)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--skip-check', action='store_true')
     args = ap.parse_args()

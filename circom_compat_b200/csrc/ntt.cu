@@ -130,17 +130,20 @@ __device__ __forceinline__ void sm_put(uint32_t* sm, uint32_t tile, uint32_t i, 
     for (int l = 0; l < 8; l++) sm[l * tile + i] = v.l[l];
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
+// 2 CTAs/SM (<= 64 registers): with one 512-thread CTA per SM every stage barrier idled the whole SM (ncu: register-limited
+// to 1 block, fmaheavy 45-52 %).  POINTWISE is a template parameter so that the plain passes do not carry the a*b accumulators.
+template <bool POINTWISE>
+__global__ void __launch_bounds__(512, 2) ntt_pass_kernel(NttPassArgs A) {
     extern __shared__ __align__(16) uint32_t sm[];
     const uint32_t tile = 1u << A.tl, half = tile >> 1, tid = threadIdx.x;
     const int cols_log = A.tl - A.k;
     const uint32_t n = 1u << A.logn;
     const uint32_t g0 = tile_global_index(tid, blockIdx.x, cols_log, A.sb, A.k);
     const uint32_t g1 = tile_global_index(tid + half, blockIdx.x, cols_log, A.sb, A.k);
-    const int nv = A.pointwise ? 3 : 1;
+    const int nv = POINTWISE ? 3 : 1;
     fe acc0 = fe_zero(), acc1 = fe_zero();
     for (int vi = 0; vi < nv; vi++) {
-        fe* vec = A.pointwise ? A.vec[vi] : A.vec[blockIdx.y];
+        fe* vec = POINTWISE ? A.vec[vi] : A.vec[blockIdx.y];
         if (tid < half || half == 0) {
             sm_put(sm, tile, tid, fe_load(&vec[g0]));
             if (half) sm_put(sm, tile, tid + half, fe_load(&vec[g1]));
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPassArgs A) {
         }
         if (tid < half || half == 0) {
             fe x0 = sm_get(sm, tile, tid), x1 = half ? sm_get(sm, tile, tid + half) : fe_zero();
-            if (!A.pointwise) {
+            if (!POINTWISE) {
                 fe_store(&vec[g0], x0);
                 if (half) fe_store(&vec[g1], x1);
             } else if (vi == 0) { acc0 = x0; acc1 = x1; }
@@ -277,7 +280,8 @@ static void launch_pass(const NttDomain& d, fe* v0, fe* v1, fe* v2, int nvec, fe
     const uint32_t ntiles = (uint32_t)(((size_t)1 << d.logn) >> d.tl);
     dim3 grid(ntiles, pointwise ? 1 : nvec);
     uint32_t threads = tile / 2 ? tile / 2 : 1;
-    ntt_pass_kernel<<<grid, threads, tile * 32, st>>>(A);
+    if (pointwise) ntt_pass_kernel<true><<<grid, threads, tile * 32, st>>>(A);
+    else ntt_pass_kernel<false><<<grid, threads, tile * 32, st>>>(A);
     g_launch_count += 1;
 }
 
