@@ -317,7 +317,7 @@ def run_ours(args):
                 "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": 2.206e9 / shard_div, "peak_source": how, "algorithmic_bytes": alg,
                 "kernel_ms": acc_ms, "whole_msm_ms": msm_ms,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^20 (profiles/r1_ncu_summary.txt, kernel id 3)",
-                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, 86 % busy in ncu, not by HBM (DESIGN.md section 5)"}
+                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, 85.5 % busy in ncu, not by HBM (DESIGN.md section 5)"}
         g2_ms, g2_acc = ctx.bench_msm(pk, cm, 4, 3)
         extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / shard_div * 160.0 / (g2_acc * 1e-3) / 1e9}
         extra["phase_ms_last_proof"] = main["timings"]
