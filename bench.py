@@ -127,9 +127,11 @@ def cpu_setup(circ):
     from circom_compat_b200 import synth
     from oracle import cref
 
+    nt = physical_cores()           # explicit: torchrun exports OMP_NUM_THREADS=1
+
     class CpuFixedBase:
-        def fixed_base_g1(self, s): return cref.fixed_base_g1(s)
-        def fixed_base_g2(self, s): return cref.fixed_base_g2(s)
+        def fixed_base_g1(self, s): return cref.fixed_base_g1(s, nt)
+        def fixed_base_g2(self, s): return cref.fixed_base_g2(s, nt)
     return synth.setup(CpuFixedBase(), circ)
 
 
@@ -141,7 +143,7 @@ def run_reference(args):
     from oracle import cref
     from circom_compat_b200 import fr_to_mont
     cref.build()
-    cores = min(cref.lib().cref_max_threads(), physical_cores())
+    cores = physical_cores()        # OpenMP num_threads() clauses; OMP_NUM_THREADS (set to 1 by torchrun) does not apply
     circ, w = build_workload(args.log_n, args.workload)
     t0 = time.time()
     pk, _ = cpu_setup(circ)
@@ -338,10 +340,10 @@ def run_ours(args):
             c_.close()
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:     # the CPU leg is reported at N = 1 only
         from oracle import cref
         cref.build()
-        cores = min(cref.lib().cref_max_threads(), physical_cores())
+        cores = physical_cores()
         za = oracle_key(pk, cm)
         t0 = time.perf_counter()
         ref = cref.prove(za, R_FIX, S_FIX, wm_np, nthreads=cores)
