@@ -61,6 +61,7 @@ struct b2g_pk {
     MsmPlan plan[NQ];
     uint32_t lo[NQ] = {}, cnt[NQ] = {}, scalar_off[NQ] = {};
     uint8_t* d_consts = nullptr;         // G1: alpha, beta, delta, a_query[0], b_g1_query[0] (5 x 64) ; G2: beta, delta, b_g2_query[0] (3 x 128)
+    void *d_tab_delta1 = nullptr, *d_tab_delta2 = nullptr;   // 8-bit window tables of delta_g1 / delta_g2 (32 x 255 affine points)
 };
 
 struct b2g_mat {
@@ -88,12 +89,31 @@ static int guarded(Fn&& fn) {
 struct Scalar256 { uint32_t l[8]; };
 
 // ------------------------------------------------------------------------------------------------ glue kernels
-// pre[0] = r*delta1, pre[1] = s*delta1, pre[2] = (r*s)*delta1 (G1 XYZZ, 128 B each); then s*delta2 (G2 XYZZ, 256 B)
-__global__ void glue_pre_kernel(const uint8_t* __restrict__ consts, Scalar256 r, Scalar256 s, uint8_t* __restrict__ pre) {
+// k * P from the 8-bit window table of P: lane w looks up digit w, a shared-memory tree adds the 32 partial points
+template <class C, class F>
+__device__ __forceinline__ typename C::Pt warp_fixed_mul(const void* __restrict__ table, const uint32_t* k, typename C::Pt* sh) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t byte = (k[lane >> 2] >> (8 * (lane & 3))) & 255u;
+    typename C::Pt v = C::infinity();
+    if (byte) v = C::from_affine(aff_load<F>(table, (size_t)lane * 255u + byte - 1u));
+    sh[lane] = v;
+    __syncwarp();
+    #pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+        if ((int)lane < d) { typename C::Pt a = sh[lane]; typename C::Pt q = sh[lane + d]; C::add(a, q); sh[lane] = a; }
+        __syncwarp();
+    }
+    return sh[0];
+}
+// pre[0] = r*delta1, pre[1] = s*delta1, pre[2] = (r*s)*delta1 (G1 XYZZ, 128 B each); then s*delta2 (G2 XYZZ, 256 B).
+// delta is fixed per key: its 8-bit window tables are built at b2g_pk_load, so each product is 32 table look-ups and a
+// 5-level tree inside one warp instead of a 254-step double-and-add on one thread (which bounded small-circuit latency).
+__global__ void __launch_bounds__(128) glue_pre_kernel(const void* __restrict__ tab_d1, const void* __restrict__ tab_d2, Scalar256 r, Scalar256 s,
+                                                       uint8_t* __restrict__ pre) {
+    __shared__ G1::Pt sh1[3][32];
+    __shared__ G2::Pt sh2[32];
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x & 31) return;
     if (warp < 3) {
-        G1::Aff d = aff_load<Fq>(consts, 2);
         Scalar256 k = (warp == 0) ? r : s;
         if (warp == 2) {
             fe rm = Fr::from_canonical(*reinterpret_cast<const fe*>(r.l)), sm = Fr::from_canonical(*reinterpret_cast<const fe*>(s.l));
@@ -101,12 +121,11 @@ __global__ void glue_pre_kernel(const uint8_t* __restrict__ consts, Scalar256 r,
             #pragma unroll
             for (int i = 0; i < 8; i++) k.l[i] = rs.l[i];
         }
-        G1::Pt p = G1::mul_scalar(G1::from_affine(d), k.l);
-        pt_store<Fq>(pre, warp, p);
+        G1::Pt p = warp_fixed_mul<G1, Fq>(tab_d1, k.l, sh1[warp]);
+        if ((threadIdx.x & 31) == 0) pt_store<Fq>(pre, warp, p);
     } else {
-        G2::Aff d = aff_load<Fq2>(consts + 5 * 64, 1);
-        G2::Pt p = G2::mul_scalar(G2::from_affine(d), s.l);
-        pt_store<Fq2>(pre + 3 * 128, 0, p);
+        G2::Pt p = warp_fixed_mul<G2, Fq2>(tab_d2, s.l, sh2);
+        if ((threadIdx.x & 31) == 0) pt_store<Fq2>(pre + 3 * 128, 0, p);
     }
 }
 
@@ -238,16 +257,19 @@ template <> struct Gen<G1> { static __device__ __forceinline__ G1::Aff get() { r
 template <> struct Gen<G2> { static __device__ __forceinline__ G2::Aff get() { return g2_generator(); } };
 
 // table[w][d-1] = d * 256^w * G (affine), w < 32, d = 1..255
+// base = nullptr: the group generator; else the affine point at `base` (e.g. delta of a proving key)
 template <class C, class F>
-__global__ void fixed_table_kernel(void* __restrict__ table) {
+__global__ void fixed_table_kernel(void* __restrict__ table, const void* __restrict__ base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 32u * 255u) return;
     uint32_t w = i / 255u, d = i % 255u + 1u;
     uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     k[w >> 2] = d << (8 * (w & 3));
-    typename C::Pt p = C::mul_scalar(C::from_affine(Gen<C>::get()), k);
+    typename C::Aff g = base ? aff_load<F>(base, 0) : Gen<C>::get();
+    typename C::Pt p = C::mul_scalar(C::from_affine(g), k);
     aff_store<F>(table, i, C::to_affine(p));
 }
+
 template <class C, class F>
 __global__ void __launch_bounds__(128) fixed_base_kernel(const void* __restrict__ table, const fe* __restrict__ scalars, uint32_t n, void* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -403,7 +425,7 @@ static Scalar256 load_scalar(const void* p) { Scalar256 s; memcpy(s.l, p, 32); r
 static void launch_glue_pre(b2g_ctx* ctx, b2g_pk* pk, const void* r, const void* s) {
     Scalar256 rr = load_scalar(r), ss = load_scalar(s);
     CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_post, 0));      // d_pre of the previous proof is no longer read
-    glue_pre_kernel<<<1, 128, 0, ctx->st_glue>>>(pk->d_consts, rr, ss, ctx->d_pre);
+    glue_pre_kernel<<<1, 128, 0, ctx->st_glue>>>(pk->d_tab_delta1, pk->d_tab_delta2, rr, ss, ctx->d_pre);
     CUDA_CHECK(cudaEventRecord(ctx->ev_pre, ctx->st_glue));
     memcpy(ctx->pre_r, rr.l, 32); memcpy(ctx->pre_s, ss.l, 32); ctx->pre_valid = true;
     g_launch_count += 1;
@@ -525,6 +547,12 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
         memcpy(&consts[192], d->a_query, 64); memcpy(&consts[256], d->b_g1_query, 64);
         memcpy(&consts[320], d->beta_g2, 128); memcpy(&consts[448], d->delta_g2, 128); memcpy(&consts[576], d->b_g2_query, 128);
         pk->d_consts = dev_upload<uint8_t>(consts.data(), consts.size(), st);
+        CUDA_CHECK(cudaMalloc(&pk->d_tab_delta1, 32 * 255 * 64));
+        CUDA_CHECK(cudaMalloc(&pk->d_tab_delta2, 32 * 255 * 128));
+        fixed_table_kernel<G1, Fq><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_delta1, pk->d_consts + 2 * 64);
+        fixed_table_kernel<G2, Fq2><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_delta2, pk->d_consts + 5 * 64 + 128);
+        g_launch_count += 2;
+        CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaStreamSynchronize(st));
         *out = pk;
     });
@@ -537,6 +565,8 @@ int b2g_pk_free(b2g_pk* pk) {
         cudaDeviceSynchronize();
         for (int q = 0; q < NQ; q++) msm_free_table(pk->plan[q]);
         if (pk->d_consts) cudaFree(pk->d_consts);
+        if (pk->d_tab_delta1) cudaFree(pk->d_tab_delta1);
+        if (pk->d_tab_delta2) cudaFree(pk->d_tab_delta2);
         delete pk;
     });
 }
@@ -887,7 +917,7 @@ static void fixed_base_entry(b2g_ctx* ctx, const void* scalars, size_t n, void* 
     cudaStream_t st = ctx->st[0];
     const size_t aff = 2 * Bytes<F>::ELEM;
     void* table = nullptr; CUDA_CHECK(cudaMalloc(&table, 32 * 255 * aff));
-    fixed_table_kernel<C, F><<<(32 * 255 + 63) / 64, 64, 0, st>>>(table);
+    fixed_table_kernel<C, F><<<(32 * 255 + 63) / 64, 64, 0, st>>>(table, nullptr);
     const size_t CH = 1u << 22;                                        // bound temporary device memory
     fe* d_sc = nullptr; uint8_t* d_out = nullptr;
     CUDA_CHECK(cudaMalloc(&d_sc, (n < CH ? n : CH) * 32)); CUDA_CHECK(cudaMalloc(&d_out, (n < CH ? n : CH) * aff));
