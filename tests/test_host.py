@@ -1,6 +1,5 @@
 """CPU tests of the host side: the C-ABI library loads and exports every declared symbol, fails loudly without a GPU,
 the host zkey reader produces the reference's structures, and the synthetic setup is a valid Groth16 key."""
-import ctypes as C
 import os
 import re
 
