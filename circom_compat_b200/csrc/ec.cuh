@@ -139,6 +139,25 @@ struct Curve {
 using G1 = Curve<Fq>;
 using G2 = Curve<Fq2>;
 
+// curve constants b (y^2 = x^3 + b): G1 b = 3, G2 b = 3 / (9 + u)   
+__device__ __forceinline__ fe curve_b(const Fq*) { fe t = fe_zero(); t.l[0] = 3; return Fq::from_canonical(t); }
+__device__ __forceinline__ fe2 curve_b(const Fq2*) {
+    fe c0, c1;
+    c0.l[0] = 0x24a138e5u; c0.l[1] = 0x3267e6dcu; c0.l[2] = 0x59dbefa3u; c0.l[3] = 0xb5b4c5e5u; c0.l[4] = 0x1be06ac3u; c0.l[5] = 0x81be1899u; c0.l[6] = 0xceb8aaaeu; c0.l[7] = 0x2b149d40u;
+    c1.l[0] = 0x85c315d2u; c1.l[1] = 0xe4a2bd06u; c1.l[2] = 0xe52d1852u; c1.l[3] = 0xa74fa084u; c1.l[4] = 0xeed8fdf4u; c1.l[5] = 0xcd2cafadu; c1.l[6] = 0x3af0fed4u; c1.l[7] = 0x009713b0u;
+    fe2 r; r.c0 = Fq::from_canonical(c0); r.c1 = Fq::from_canonical(c1);
+    return r;
+}
+// on-curve test of an affine point (infinity = all zero is accepted): the check G1Affine::new / G2Affine::new performs
+// when the reference parses a zkey (/root/reference/src/zkey.rs:340-360, panics if it fails)
+template <class C, class F>
+__device__ __forceinline__ bool aff_on_curve(const Affine<F>& p) {
+    if (C::aff_is_inf(p)) return true;
+    typename F::elem lhs = F::sqr(p.y);
+    typename F::elem rhs = F::add(F::mul(F::sqr(p.x), p.x), curve_b((const F*)nullptr));
+    return F::eq(lhs, rhs);
+}
+
 // ---------------------------------------------------------------------------------------------- memory layout helpers
 // G1 affine = 64 B (x||y), G2 affine = 128 B (x.c0||x.c1||y.c0||y.c1); XYZZ = 4 coordinates back to back.
 __device__ __forceinline__ void elem_load(fe& r, const void* p) { r = fe_load(p); }

@@ -41,6 +41,14 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const void* __restrict__
     }
 }
 
+// every base must be on the curve (or the all-zero point at infinity); *bad receives 1 + index of an offender
+template <class C, class F>
+__global__ void __launch_bounds__(256) msm_validate_kernel(const void* __restrict__ bases, uint32_t n, uint32_t* __restrict__ bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!aff_on_curve<C, F>(aff_load<F>(bases, i))) atomicMax(bad, i + 1u);
+}
+
 // ------------------------------------------------------------------------------------------------ (1) digits + histogram
 // (1a) scalars -> canonical integers (one Montgomery reduction each)
 __global__ void __launch_bounds__(256) msm_canon_kernel(const fe* __restrict__ scalars, uint32_t n, int scalars_mont, fe* __restrict__ canon_out) {
@@ -307,8 +315,18 @@ static void msm_build_table_t(MsmPlan& plan, const void* bases_dev, uint32_t n, 
     plan.n = n; plan.c = (int)env_u32("B2G_MSM_C", (uint32_t)msm_pick_c(n ? n : 1)); plan.nwin = msm_nwin(plan.c); plan.nbuckets = 1u << (plan.c - 1);
     if (n == 0) { plan.table = nullptr; return; }
     if ((uint64_t)n * plan.nwin >= (1ull << 31)) throw_error(B2G_E_SHAPE, "msm: n * windows exceeds 2^31 table rows");
+    // reference behaviour: an off-curve point in a zkey makes G1Affine::new panic (src/zkey.rs:347); here: B2G_E_INPUT
+    uint32_t* d_bad = nullptr; uint32_t bad = 0;
+    CUDA_CHECK(cudaMalloc(&d_bad, 4));
+    CUDA_CHECK(cudaMemsetAsync(d_bad, 0, 4, st));
+    msm_validate_kernel<C, F><<<(n + 255) / 256, 256, 0, st>>>(bases_dev, n, d_bad);
+    CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d_bad);
+    if (bad) throw_error(B2G_E_INPUT, std::string(plan.g2 ? "G2" : "G1") + " base " + std::to_string(bad - 1) + " of the query slice is not on the curve");
     CUDA_CHECK(cudaMalloc(&plan.table, (size_t)n * plan.nwin * aff));
     msm_table_kernel<C, F><<<(n + 127) / 128, 128, 0, st>>>(bases_dev, n, plan.c, plan.nwin, plan.table);
+    g_launch_count += 2;
     CUDA_CHECK(cudaGetLastError());
 }
 
