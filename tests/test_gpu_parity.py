@@ -467,3 +467,19 @@ def test_sharded_proof_fused_peer_memory_exchange():
     res = sorted(q.get(timeout=150) for _ in range(2))
     [p.join(timeout=30) for p in procs]
     assert res == [(0, True), (1, True)], res
+
+
+def test_off_curve_key_point_is_rejected(ctx, test_zkey_bytes):
+    # the reference panics in G1Affine::new on an off-curve zkey point (src/zkey.rs:347); the ABI returns B2G_E_INPUT
+    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, B2gError, release
+    pk, cm = read_zkey(test_zkey_bytes)
+    pk.a_query = pk.a_query.copy(); pk.a_query[2, 0] ^= 1          # flip one bit of a coordinate
+    with pytest.raises(B2gError) as e:
+        Groth16.create_proof_with_reduction_and_matrices(pk, 1, 1, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont([1, 33, 3, 11]), ctx)
+    assert e.value.code == -4 and 'not on the curve' in str(e.value)
+    pk2, _ = read_zkey(test_zkey_bytes)
+    pk2.b_g2_query = pk2.b_g2_query.copy(); pk2.b_g2_query[3, 5] ^= 4
+    with pytest.raises(B2gError) as e:
+        ctx.pk_handle(pk2)
+    assert e.value.code == -4
+    release(cm)
