@@ -483,3 +483,78 @@ def test_off_curve_key_point_is_rejected(ctx, test_zkey_bytes):
         ctx.pk_handle(pk2)
     assert e.value.code == -4
     release(cm)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def _prove_both(ctx, circ, w, r, s, td_seed=7):
+    """GPU proof and CPU-oracle proof on a fresh synthetic key; returns (gpu bytes, oracle bytes, pk, td)"""
+    from circom_compat_b200 import Groth16, fr_to_mont, synth, release
+    pk, td = synth.setup(ctx, circ, seed=td_seed)
+    cm = circ.matrices()
+    wm = fr_to_mont(w)
+    p = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    ref = c.prove(_oracle_key(pk, cm), r, s, wm)
+    release(pk); release(cm)
+    return p, ref
+
+
+def test_edge_zero_witness_and_zero_blinding(ctx):
+    # squaring chain with a = 0: every wire except the constant is 0 -> all MSM scalars but one vanish (empty buckets,
+    # infinity partial results); r = s = 0 removes every delta term and skips B1 (prover.rs: r == 0)
+    from circom_compat_b200 import synth
+    circ = synth.chain_circuit(1 << 10)
+    w = synth.chain_witness(1 << 10, 0)
+    assert w[0] == 1 and not any(w[1:])
+    for r, s in ((0, 0), (0, 5), (7, 0), (o.R_MOD - 1, o.R_MOD - 1)):
+        p, ref = _prove_both(ctx, circ, w, r, s)
+        assert p.data == ref, (r, s)
+
+
+def test_edge_no_witness_variables_and_tiny_domains(ctx):
+    # n_vars == num_inputs: the L query is empty (msm over zero terms = infinity); domains of size 2 and 4
+    from circom_compat_b200 import synth
+    one = [1]
+    circ = synth.Circuit(2, 2, 1, (np.array([0]), np.array([1]), one), (np.array([0]), np.array([0]), one), (np.array([0]), np.array([1]), one))   # w1 * 1 = w1
+    w = [1, 5]
+    assert circ.domain_size == 4
+    p, ref = _prove_both(ctx, circ, w, 3, 4)
+    assert p.data == ref
+    circ1 = synth.Circuit(1, 1, 1, (np.array([0]), np.array([0]), one), (np.array([0]), np.array([0]), one), (np.array([0]), np.array([0]), one))  # 1 * 1 = 1
+    assert circ1.domain_size == 2
+    p, ref = _prove_both(ctx, circ1, [1], 9, 11)
+    assert p.data == ref
+
+
+@pytest.mark.parametrize('m', [1022, 1023, 1024])
+def test_edge_domain_boundaries(ctx, m):
+    # domain = next_pow2(num_constraints + num_inputs) (qap.rs:30-31): 1022 + 2 = 1024 exactly, 1023 + 2 and 1024 + 2 -> 2048
+    from circom_compat_b200 import synth
+    circ = synth.chain_circuit(m + 2)
+    assert circ.num_constraints == m and circ.domain_size == (1024 if m == 1022 else 2048)
+    p, ref = _prove_both(ctx, circ, synth.chain_witness(m + 2, 3), 0xabcdef, 0x123456)
+    assert p.data == ref
+
+
+def test_edge_ragged_rows_and_repeated_columns(ctx):
+    # rows with 0, 1 and many terms, repeated wire indices and explicit zero coefficients in A / B (evaluate_constraint just sums)
+    from circom_compat_b200 import synth, CircomReduction, fr_to_mont, release
+    rng = random.Random(31)
+    n_vars, li, m = 40, 3, 29
+    w = [1] + [rng.randrange(o.R_MOD) for _ in range(n_vars - 1)]
+    rows_a, cols_a, vals_a, rows_b, cols_b, vals_b = [], [], [], [], [], []
+    for i in range(m):
+        for (rows, cols, vals, k) in ((rows_a, cols_a, vals_a, i % 7), (rows_b, cols_b, vals_b, (i * 3) % 5)):
+            for _ in range(k):                                   # k = 0 -> empty row
+                rows.append(i); cols.append(rng.randrange(n_vars)); vals.append(rng.choice([0, 1, o.R_MOD - 1, rng.randrange(o.R_MOD)]))
+    circ = synth.Circuit(n_vars, li, m, (np.array(rows_a), np.array(cols_a), vals_a), (np.array(rows_b), np.array(cols_b), vals_b),
+                         (np.array([], dtype=np.int64), np.array([], dtype=np.int64), []))
+    cm = circ.matrices()
+    wm = fr_to_mont(w)
+    h = CircomReduction.witness_map_from_matrices(cm, li, m, wm, ctx)
+    href = c.witness_map(m, li, n_vars, cm.a, cm.b, wm)
+    assert np.array_equal(h, href)
+    A = [[] for _ in range(m)]; B = [[] for _ in range(m)]
+    for r_, c_, v in zip(rows_a, cols_a, vals_a): A[r_].append((v, c_))
+    for r_, c_, v in zip(rows_b, cols_b, vals_b): B[r_].append((v, c_))
+    assert c.limbs_to_ints(c.fr_from_mont(h)) == o.witness_map_from_matrices(A, B, li, m, w)
+    release(cm)
