@@ -104,7 +104,13 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
     const uint32_t tid = threadIdx.x, per = (nb + 1023u) / 1024u;
     const uint32_t lo = tid * per, hi = min(lo + per, nb);
     uint32_t s = 0;
-    for (uint32_t j = lo; j < hi; j++) s += counts[j];
+    if ((per & 3u) == 0 && hi == lo + per) {                      // aligned chunk: independent 128-bit loads
+        const uint4* v4 = reinterpret_cast<const uint4*>(counts + lo);
+        #pragma unroll 4
+        for (uint32_t j = 0; j < per / 4; j++) { const uint4 q = __ldg(&v4[j]); s += q.x + q.y + q.z + q.w; }
+    } else {
+        for (uint32_t j = lo; j < hi; j++) s += counts[j];
+    }
     // block exclusive scan of s
     uint32_t v = s;
     #pragma unroll
