@@ -7,4 +7,5 @@ read_zkey, ProvingKey, ConstraintMatrices, CircomReduction, Groth16.  All arithm
 from .zkey import read_zkey, ProvingKey, ConstraintMatrices, fr_to_mont, fr_from_mont  # noqa: F401
 from .groth16 import Groth16, CircomReduction, LibsnarkReduction, Proof, Context, release, release_all  # noqa: F401
 from .r1cs import R1CSFile, R1CS, read_wtns  # noqa: F401
+from .builder import CircomConfig, CircomBuilder, CircomCircuit  # noqa: F401
 from ._native import B2gError, PolynomialDegreeTooLarge  # noqa: F401

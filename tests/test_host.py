@@ -229,3 +229,30 @@ def test_libsnark_oracles_agree_and_satisfy_qap_identity():
     cm = r.to_circuit().matrices(with_c=True)
     hc = c.witness_map_libsnark(cm.num_constraints, cm.num_instance_variables, cm.a, cm.b, cm.c, fr_to_mont(w))
     assert c.limbs_to_ints(c.fr_from_mont(hc)) == h
+
+
+def test_builder_api_surface():
+    """CircomConfig / CircomBuilder / CircomCircuit flow of /root/reference/tests/groth16.rs:11-41 (witness from a callable
+    standing in for the WASM calculator) and :106-119 (witness generation only)."""
+    from circom_compat_b200 import CircomConfig, CircomBuilder
+    g = os.path.join(ROOT, 'tests', 'golden')
+
+    def mycircuit_calculator(inputs):                      # test-vectors/mycircuit.circom: c <== a * b
+        a, b = inputs['a'][0], inputs['b'][0]
+        return [1, a * b, a, b]
+    cfg = CircomConfig.new(mycircuit_calculator, os.path.join(g, 'mycircuit.r1cs'))
+    builder = CircomBuilder.new(cfg)
+    builder.push_input('a', 3)
+    builder.push_input('b', 11)
+    circom = builder.setup()
+    assert circom.witness is None and circom.get_public_inputs() is None and circom.r1cs.wire_mapping is None
+    circom = builder.build()
+    assert circom.witness == [1, 33, 3, 11] and circom.get_public_inputs() == [33]
+    bad = CircomBuilder.new(CircomConfig.new(lambda inputs: [1, 34, 3, 11], os.path.join(g, 'mycircuit.r1cs')))
+    with pytest.raises(ValueError):
+        bad.build()
+    # .wtns file as the witness source (circuit2, 131 constraints: tests/groth16.rs:75-105)
+    c2 = CircomBuilder.new(CircomConfig.new(os.path.join(g, 'circuit2_witness.wtns'), os.path.join(g, 'circuit2.r1cs'))).build()
+    assert len(c2.witness) == 132 and c2.get_public_inputs() == [33]
+    circ = c2.to_circuit()
+    assert circ.num_constraints == 131 and circ.num_inputs == 2
