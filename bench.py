@@ -239,12 +239,16 @@ def run_ours(args):
                 return Groth16.prove_sharded_p2p(pk, cm, R_FIX, S_FIX, wms[i], ctxs[i])
             return sharding.prove_sharded(ctxs[i], pk, cm, wms[i], R_FIX, S_FIX, dist, dev, groups[i])
 
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=inflight)          # persistent host threads: one per in-flight proof
+
         def run_steps(total):
-            res = [None] * inflight
             def worker(i):
+                last = None
                 for _ in range(total // inflight + (1 if i < total % inflight else 0)):
-                    res[i] = one_proof(i)
-            threads(worker, inflight)
+                    last = one_proof(i)
+                return last
+            res = list(pool.map(worker, range(inflight)))
             return res[0]
 
         t0 = time.time()
@@ -288,6 +292,7 @@ def run_ours(args):
             barrier()
             res["latency_ms"] = max_over_ranks((time.perf_counter() - t0) / 5 * 1e3)
         res["clocks"] = sampler.stop() if rank == 0 else None
+        pool.shutdown()
         return res
 
     main_mode = 'single' if world == 1 else args.mode
