@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(128) glue_pre_kernel(const void* __restrict__ 
     if (warp < 3) {
         Scalar256 k = (warp == 0) ? r : s;
         if (warp == 2) {
-            fe rm = Fr::from_canonical(*reinterpret_cast<const fe*>(r.l)), sm = Fr::from_canonical(*reinterpret_cast<const fe*>(s.l));
+            fe rc, sc;                                   // Scalar256 is only 4-byte aligned: copy limb by limb
+            #pragma unroll
+            for (int i = 0; i < 8; i++) { rc.l[i] = r.l[i]; sc.l[i] = s.l[i]; }
+            fe rm = Fr::from_canonical(rc), sm = Fr::from_canonical(sc);
             fe rs = Fr::to_canonical(Fr::mul(rm, sm));
             #pragma unroll
             for (int i = 0; i < 8; i++) k.l[i] = rs.l[i];

@@ -71,11 +71,13 @@ class ConstraintMatrices:
 
 
 def _sections(data):
-    if bytes(data[:4]) != b'zkey':
+    if len(data) < 12 or bytes(data[:4]) != b'zkey':
         raise ValueError("not a zkey file")
     nsec = struct.unpack_from('<I', data, 8)[0]
     pos, sec = 12, {}
     for _ in range(nsec):                                           # src/zkey.rs:73-101
+        if pos + 12 > len(data):
+            raise ValueError("malformed zkey: truncated section table")
         sid, slen = struct.unpack_from('<IQ', data, pos)
         pos += 12
         sec.setdefault(sid, (pos, slen))
@@ -102,6 +104,11 @@ def read_zkey(src):
     else:
         raise TypeError("read_zkey expects a path, bytes or a binary reader")
     sec = _sections(data)
+    for sid in (2, 3, 4, 5, 6, 7, 8, 9):
+        if sid not in sec:
+            raise ValueError(f"malformed zkey: section {sid} missing")
+        if sec[sid][0] + sec[sid][1] > len(data):
+            raise ValueError(f"malformed zkey: section {sid} is truncated")
     p = sec[2][0]                                                   # header, src/zkey.rs:282-318
     n8q = struct.unpack_from('<I', data, p)[0]; p += 4
     q = int.from_bytes(data[p:p + n8q], 'little'); p += n8q

@@ -256,3 +256,35 @@ def test_builder_api_surface():
     assert len(c2.witness) == 132 and c2.get_public_inputs() == [33]
     circ = c2.to_circuit()
     assert circ.num_constraints == 131 and circ.num_inputs == 2
+
+
+# ------------------------------------------------------------------------------------------------ malformed inputs
+def test_truncated_and_corrupt_files_fail_cleanly(tmp_path, test_zkey_bytes):
+    """A malformed .zkey / .r1cs / .wtns must raise (Python) or exit with an error message (C++ reader), never crash:
+    the reference returns SerializationError for these (src/zkey.rs:43, r1cs_reader.rs:13)."""
+    import subprocess
+    from circom_compat_b200 import read_zkey, R1CSFile, read_wtns
+    g = os.path.join(ROOT, 'tests', 'golden')
+    r1cs = open(os.path.join(g, 'mycircuit.r1cs'), 'rb').read()
+    wtns = open(os.path.join(g, 'circuit2_witness.wtns'), 'rb').read()
+    for cut in (3, 11, 40, 700, len(test_zkey_bytes) - 200):          # the last 104 bytes are the unread contributions section
+        with pytest.raises(Exception):
+            read_zkey(test_zkey_bytes[:cut])
+        f = tmp_path / ('t%d.zkey' % cut)
+        f.write_bytes(test_zkey_bytes[:cut])
+        r = subprocess.run([HOST_BIN, '--parse-only', str(f)], capture_output=True, text=True, timeout=30)
+        assert r.returncode == 1 and 'error:' in r.stderr, (cut, r.returncode, r.stderr)
+    bad = bytearray(test_zkey_bytes); bad[0:4] = b'r1cs'
+    with pytest.raises(ValueError):
+        read_zkey(bytes(bad))
+    wrong_curve = bytearray(test_zkey_bytes)
+    from circom_compat_b200.zkey import _sections
+    wrong_curve[_sections(test_zkey_bytes)[2][0] + 4] ^= 1               # first byte of q in the header section
+    with pytest.raises(ValueError):
+        read_zkey(bytes(wrong_curve))
+    for cut in (2, 20, 100, len(r1cs) - 5):
+        with pytest.raises(Exception):
+            R1CSFile.new(r1cs[:cut])
+    for cut in (2, 30, 60):
+        with pytest.raises(Exception):
+            read_wtns(wtns[:cut])
