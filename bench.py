@@ -321,21 +321,24 @@ def run_ours(args):
         msm_ms, acc_ms = ctx.bench_msm(pk, cm, 0, 5)
         alg = pk.domain_size // shard_div * 96.0
         roof = {"bound": "hbm", "kernel": "msm_accumulate_kernel<G1> (H query)", "achieved": alg / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": 2.206e9 / shard_div, "peak_source": how, "algorithmic_bytes": alg,
+                "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": 2.076e9 / shard_div, "peak_source": how, "algorithmic_bytes": alg,
                 "kernel_ms": acc_ms, "whole_msm_ms": msm_ms,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^20 (profiles/r1_ncu_summary.txt, kernel id 3)",
-                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, 85.5 % busy in ncu, not by HBM (DESIGN.md section 5)"}
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^20 (profiles/r1_ncu_summary_final.txt, kernel id 11)",
+                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, 85.4 % busy in ncu, not by HBM (DESIGN.md section 5)"}
         # the binding roofline: IMAD.WIDE issue slots (fmaheavy pipe).  Slots per mixed add are a static property of the
-        # kernel (ncu: 85.5 % of 5.18 M cycles/SMSP busy -> 1250 IMAD.WIDE-equivalents per G1 add); adds per launch = digits
-        # that are non-zero (here all n * nwin); peak = 148 SMs x 4 SMSPs x 32 lanes / 4 cycles x 1.965 GHz.
-        nwin = 16 if args.log_n >= 19 else None
-        if nwin:
-            adds = (pk.domain_size // shard_div) * nwin
+        # kernel (ncu: 85.4 % of 4.66 M cycles/SMSP busy over 15 x 2^20 adds -> 1198 IMAD.WIDE-equivalents per G1 add);
+        # adds per launch = non-zero digits (here all n * windows, windows = ceil(255 / c) with the library's window rule);
+        # peak = 148 SMs x 4 SMSPs x 32 lanes / 4 cycles x 1.965 GHz.
+        n_h = pk.domain_size // shard_div
+        if args.log_n >= 19 and not os.environ.get('B2G_MSM_C'):
+            c_win = 17 if n_h >= (3 << 18) else 16                  # msm_pick_c (csrc/msm.cuh)
+            nwin = -(-255 // c_win)
+            adds = n_h * nwin
             peak_int = 148 * 4 * 32 / 4 * 1.965e9
-            ach_int = adds * 1250.0 / (acc_ms * 1e-3)
+            ach_int = adds * 1198.0 / (acc_ms * 1e-3)
             roof["int_pipe"] = {"bound": "IMAD.WIDE issue (fmaheavy pipe)", "achieved": ach_int / 1e12, "peak": peak_int / 1e12, "unit": "T IMAD.WIDE/s",
-                                "frac": ach_int / peak_int, "mixed_adds_per_launch": adds, "imad_wide_per_add": 1250,
-                                "source": "adds x static IMAD.WIDE count / live CUDA-event kernel time; count and peak rate from profiles/r1_ncu_summary.txt"}
+                                "frac": ach_int / peak_int, "mixed_adds_per_launch": adds, "windows": nwin, "window_bits": c_win, "imad_wide_per_add": 1198,
+                                "source": "adds x IMAD.WIDE-equivalents per add / live CUDA-event kernel time; count and peak rate from profiles/r1_ncu_summary_final.txt"}
         g2_ms, g2_acc = ctx.bench_msm(pk, cm, 4, 3)
         extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / shard_div * 160.0 / (g2_acc * 1e-3) / 1e9}
         extra["phase_ms_last_proof"] = main["timings"]

@@ -239,12 +239,257 @@ struct Fp {
               "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
         return reduce_once(r);
     }
-    static __device__ __forceinline__ fe sqr(const fe& a) { return mul(a, a); }
+    // defined after the lazy-reduction blocks: sqr(a) = redc(sqr_wide(a)), 36 + 64 products instead of 128
+    static __device__ __forceinline__ fe sqr(const fe& a) {
+#ifdef B2G_SQR_IS_MUL
+        return mul(a, a);
+#else
+        uint32_t t[16];
+        sqr_wide(t, a);
+        return redc(t);
+#endif
+    }
 
     // ------------------------------------------------------------------ lazy-reduction building blocks (used by Fq2)
-    // t[0..15] = a * b as a plain 512-bit integer (a, b any 256-bit values).  Schoolbook on even/odd column accumulators:
-    // every 8-limb carry chain ends in a limb that so far holds at most a few carries, so one addc closes it.
+    // one row of the plain 256 x 32 product, same column bookkeeping as row() but without the reduction step:
+    // after the call x[0] is a finished limb of the result and x[1..7], e[0..7] carry the rest one limb further up.
+    static __device__ __forceinline__ void prow(uint32_t* x, uint32_t* e, const fe& a, uint32_t b, bool first) {
+        if (first) {
+            mul4(e, a.l[1], a.l[3], a.l[5], a.l[7], b);
+            mul4(x, a.l[0], a.l[2], a.l[4], a.l[6], b);
+        } else {
+            madc_shift(x[0], e, a.l[1], a.l[3], a.l[5], a.l[7], b);
+            cmad4(x, e[7], a.l[0], a.l[2], a.l[4], a.l[6], b);
+        }
+    }
+    // t[0..15] = a * b as a plain 512-bit integer, a < 2^255 (so that the top column never overflows), b any 256-bit
+    // value.  Eight rows; each retires one low limb, so there is one closing addc per row and no zero-initialisation.
     static __device__ __forceinline__ void mul_wide(uint32_t* t, const fe& a, const fe& b) {
+        uint32_t ev[8], od[8];
+        prow(ev, od, a, b.l[0], true);  t[0] = ev[0];
+        prow(od, ev, a, b.l[1], false); t[1] = od[0];
+        prow(ev, od, a, b.l[2], false); t[2] = ev[0];
+        prow(od, ev, a, b.l[3], false); t[3] = od[0];
+        prow(ev, od, a, b.l[4], false); t[4] = ev[0];
+        prow(od, ev, a, b.l[5], false); t[5] = od[0];
+        prow(ev, od, a, b.l[6], false); t[6] = ev[0];
+        prow(od, ev, a, b.l[7], false); t[7] = od[0];
+        // od is limb-7 aligned with od[0] retired, ev is limb-8 aligned: high half = ev + (od >> 32)
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, 0;"
+            : "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+            : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+              "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+    }
+
+    // ---- squaring: a^2 = sum_j a_j 2^(32j) [ (a_j + topbit(a_(j-1))) 2^(32j) + sum_(i<j) b_i 2^(32i) ],  b = limbs of 2a.
+    // 36 products instead of 64, no doubling pass; each carry chain ends on two fresh limbs, so nothing has to be closed.
+    // f = x * y + add
+    static __device__ __forceinline__ void chain1(uint32_t* f, uint32_t x, uint32_t y, uint32_t add) {
+        asm("mad.lo.cc.u32 %0, %2, %3, %4;\n\t madc.hi.u32 %1, %2, %3, 0;" : "=&r"(f[0]), "=&r"(f[1]) : "r"(x), "r"(y), "r"(add));
+    }
+    // acc[0..1] += x0 * y ; acc[2..3] = x1 * y + add (+ carry)
+    static __device__ __forceinline__ void chain2(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t y, uint32_t add) {
+        asm("mad.lo.cc.u32 %0, %4, %6, %0;\n\t madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+            "madc.lo.cc.u32 %2, %5, %6, %7;\n\t madc.hi.u32 %3, %5, %6, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "=&r"(acc[2]), "=&r"(acc[3]) : "r"(x0), "r"(x1), "r"(y), "r"(add));
+    }
+    static __device__ __forceinline__ void chain3(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y, uint32_t add) {
+        asm("mad.lo.cc.u32 %0, %6, %9, %0;\n\t madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %7, %9, %2;\n\t madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+            "madc.lo.cc.u32 %4, %8, %9, %10;\n\t madc.hi.u32 %5, %8, %9, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=&r"(acc[4]), "=&r"(acc[5])
+            : "r"(x0), "r"(x1), "r"(x2), "r"(y), "r"(add));
+    }
+    static __device__ __forceinline__ void chain4(uint32_t* acc, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y, uint32_t add) {
+        asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9, %12, %2;\n\t madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+            "madc.lo.cc.u32 %4, %10, %12, %4;\n\t madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+            "madc.lo.cc.u32 %6, %11, %12, %13;\n\t madc.hi.u32 %7, %11, %12, 0;"
+            : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=&r"(acc[6]), "=&r"(acc[7])
+            : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y), "r"(add));
+    }
+    // t[0..15] = a^2 (any 256-bit a)
+    static __device__ __forceinline__ void sqr_wide(uint32_t* t, const fe& a) {
+        uint32_t b[7], m[8], ev[16], od[14];
+        b[0] = a.l[0] << 1;
+        #pragma unroll
+        for (int i = 1; i < 7; i++) b[i] = __funnelshift_l(a.l[i - 1], a.l[i], 1);
+        #pragma unroll
+        for (int j = 1; j < 8; j++) m[j] = a.l[j] & (uint32_t)((int32_t)a.l[j - 1] >> 31);
+        // columns at even limb positions: a_j * (b_i, i = j-2, j-4, ...) then a_j * a_j + m_j on fresh limbs 2j, 2j+1
+        chain1(&ev[0], a.l[0], a.l[0], 0);
+        chain1(&ev[2], a.l[1], a.l[1], m[1]);
+        chain2(&ev[2], b[0], a.l[2], a.l[2], m[2]);
+        chain2(&ev[4], b[1], a.l[3], a.l[3], m[3]);
+        chain3(&ev[4], b[0], b[2], a.l[4], a.l[4], m[4]);
+        chain3(&ev[6], b[1], b[3], a.l[5], a.l[5], m[5]);
+        chain4(&ev[6], b[0], b[2], b[4], a.l[6], a.l[6], m[6]);
+        chain4(&ev[8], b[1], b[3], b[5], a.l[7], a.l[7], m[7]);
+        // columns at odd limb positions (od[k] sits at limb k + 1): a_j * (b_i, i = j-1, j-3, ...)
+        chain1(&od[0], b[0], a.l[1], 0);
+        chain1(&od[2], b[1], a.l[2], 0);
+        chain2(&od[2], b[0], b[2], a.l[3], 0);
+        chain2(&od[4], b[1], b[3], a.l[4], 0);
+        chain3(&od[4], b[0], b[2], b[4], a.l[5], 0);
+        chain3(&od[6], b[1], b[3], b[5], a.l[6], 0);
+        chain4(&od[6], b[0], b[2], b[4], b[6], a.l[7], 0);
+        t[0] = ev[0];
+        asm("add.cc.u32 %0, %15, %30;\n\t"
+            "addc.cc.u32 %1, %16, %31;\n\t"
+            "addc.cc.u32 %2, %17, %32;\n\t"
+            "addc.cc.u32 %3, %18, %33;\n\t"
+            "addc.cc.u32 %4, %19, %34;\n\t"
+            "addc.cc.u32 %5, %20, %35;\n\t"
+            "addc.cc.u32 %6, %21, %36;\n\t"
+            "addc.cc.u32 %7, %22, %37;\n\t"
+            "addc.cc.u32 %8, %23, %38;\n\t"
+            "addc.cc.u32 %9, %24, %39;\n\t"
+            "addc.cc.u32 %10, %25, %40;\n\t"
+            "addc.cc.u32 %11, %26, %41;\n\t"
+            "addc.cc.u32 %12, %27, %42;\n\t"
+            "addc.cc.u32 %13, %28, %43;\n\t"
+            "addc.u32 %14, %29, 0;"
+            : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
+              "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+            : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]),
+              "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+              "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]),
+              "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]));
+    }
+
+    // t -= u  (512-bit); returns the borrow mask (0xffffffff when t < u)
+    static __device__ __forceinline__ uint32_t sub_wide(uint32_t* t, const uint32_t* u) {
+        uint32_t br;
+        asm("sub.cc.u32 %0, %0, %17;\n\t"
+            "subc.cc.u32 %1, %1, %18;\n\t"
+            "subc.cc.u32 %2, %2, %19;\n\t"
+            "subc.cc.u32 %3, %3, %20;\n\t"
+            "subc.cc.u32 %4, %4, %21;\n\t"
+            "subc.cc.u32 %5, %5, %22;\n\t"
+            "subc.cc.u32 %6, %6, %23;\n\t"
+            "subc.cc.u32 %7, %7, %24;\n\t"
+            "subc.cc.u32 %8, %8, %25;\n\t"
+            "subc.cc.u32 %9, %9, %26;\n\t"
+            "subc.cc.u32 %10, %10, %27;\n\t"
+            "subc.cc.u32 %11, %11, %28;\n\t"
+            "subc.cc.u32 %12, %12, %29;\n\t"
+            "subc.cc.u32 %13, %13, %30;\n\t"
+            "subc.cc.u32 %14, %14, %31;\n\t"
+            "subc.cc.u32 %15, %15, %32;\n\t"
+            "subc.u32 %16, 0, 0;"
+            : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
+              "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15]), "=r"(br)
+            : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+              "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]));
+        return br;
+    }
+
+    // t += u  (512-bit, carry out discarded)
+    static __device__ __forceinline__ void add_wide(uint32_t* t, const uint32_t* u) {
+        asm("add.cc.u32 %0, %0, %16;\n\t"
+            "addc.cc.u32 %1, %1, %17;\n\t"
+            "addc.cc.u32 %2, %2, %18;\n\t"
+            "addc.cc.u32 %3, %3, %19;\n\t"
+            "addc.cc.u32 %4, %4, %20;\n\t"
+            "addc.cc.u32 %5, %5, %21;\n\t"
+            "addc.cc.u32 %6, %6, %22;\n\t"
+            "addc.cc.u32 %7, %7, %23;\n\t"
+            "addc.cc.u32 %8, %8, %24;\n\t"
+            "addc.cc.u32 %9, %9, %25;\n\t"
+            "addc.cc.u32 %10, %10, %26;\n\t"
+            "addc.cc.u32 %11, %11, %27;\n\t"
+            "addc.cc.u32 %12, %12, %28;\n\t"
+            "addc.cc.u32 %13, %13, %29;\n\t"
+            "addc.cc.u32 %14, %14, %30;\n\t"
+            "addc.u32 %15, %15, %31;"
+            : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
+              "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+            : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+              "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]));
+    }
+
+    // high half of t += p & mask  (adds p * 2^256 when mask is all ones)
+    static __device__ __forceinline__ void add_p_high(uint32_t* t, uint32_t mask) {
+        uint32_t m0 = P::P0 & mask, m1 = P::P1 & mask, m2 = P::P2 & mask, m3 = P::P3 & mask,
+                 m4 = P::P4 & mask, m5 = P::P5 & mask, m6 = P::P6 & mask, m7 = P::P7 & mask;
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
+            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(m6), "r"(m7));
+    }
+
+    // x0 += e[1]; m = x0 * INV; e[j], e[j+1] = {p_odd * m} + e[j+2], e[j+3]  (the reduction row's counterpart of madc_shift;
+    // m is computed between the first add and the multiply-add chain, which mul.lo leaves the carry flag alone for)
+    static __device__ __forceinline__ void madc_shift_m(uint32_t& x0, uint32_t* e, uint32_t& m) {
+        asm("add.cc.u32 %8, %8, %1;\n\t"
+            "mul.lo.u32 %9, %8, %10;\n\t"
+            "madc.lo.cc.u32 %0, %11, %9, %2;\n\t madc.hi.cc.u32 %1, %11, %9, %3;\n\t"
+            "madc.lo.cc.u32 %2, %12, %9, %4;\n\t madc.hi.cc.u32 %3, %12, %9, %5;\n\t"
+            "madc.lo.cc.u32 %4, %13, %9, %6;\n\t madc.hi.cc.u32 %5, %13, %9, %7;\n\t"
+            "madc.lo.cc.u32 %6, %14, %9, 0;\n\t madc.hi.u32 %7, %14, %9, 0;"
+            : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(x0), "=&r"(m)
+            : "r"(P::INV), "r"(P::P1), "r"(P::P3), "r"(P::P5), "r"(P::P7));
+    }
+    // one reduction row: x is limb-0 aligned, e becomes the limb-1 aligned array; x[0] ends up 0
+    static __device__ __forceinline__ void mrow(uint32_t* x, uint32_t* e) {
+        uint32_t m;
+        madc_shift_m(x[0], e, m);
+        cmad4(x, e[7], P::P0, P::P2, P::P4, P::P6, m);
+    }
+    // Montgomery reduction of a 512-bit t < p * 2^256: returns (t + M p) / 2^256 reduced once, i.e. in [0, p)
+    // (the value before the subtraction is < t / 2^256 + p < 2p).  The low half is folded with the same even/odd column
+    // rows as mul(); the high half is added at the end.
+    static __device__ __forceinline__ fe redc(const uint32_t* t) {
+        uint32_t ev[8], od[8];
+        #pragma unroll
+        for (int i = 0; i < 8; i++) ev[i] = t[i];
+        {
+            const uint32_t m = ev[0] * P::INV;
+            mul4(od, P::P1, P::P3, P::P5, P::P7, m);
+            cmad4(ev, od[7], P::P0, P::P2, P::P4, P::P6, m);
+        }
+        mrow(od, ev); mrow(ev, od); mrow(od, ev); mrow(ev, od); mrow(od, ev); mrow(ev, od); mrow(od, ev);
+        // od is limb-0 aligned with od[0] == 0, ev is limb-1 aligned: r = ev + (od >> 32) + t[8..15]   (< 2p, no carry out)
+        fe r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, 0;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(ev[0]), "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+              "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+            : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+        return reduce_once(r);
+    }
+
+    // ---- first-generation forms (independent column chains / per-row shift adds): more ALU work, more ILP
+    static __device__ __forceinline__ void mul_wide_v1(uint32_t* t, const fe& a, const fe& b) {
         uint32_t ev[17], od[16];
         #pragma unroll
         for (int i = 0; i < 17; i++) ev[i] = 0;
@@ -284,52 +529,7 @@ struct Fp {
               "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
     }
 
-    // t -= u  (512-bit); returns the borrow mask (0xffffffff when t < u)
-    static __device__ __forceinline__ uint32_t sub_wide(uint32_t* t, const uint32_t* u) {
-        uint32_t br;
-        asm("sub.cc.u32 %0, %0, %17;\n\t"
-            "subc.cc.u32 %1, %1, %18;\n\t"
-            "subc.cc.u32 %2, %2, %19;\n\t"
-            "subc.cc.u32 %3, %3, %20;\n\t"
-            "subc.cc.u32 %4, %4, %21;\n\t"
-            "subc.cc.u32 %5, %5, %22;\n\t"
-            "subc.cc.u32 %6, %6, %23;\n\t"
-            "subc.cc.u32 %7, %7, %24;\n\t"
-            "subc.cc.u32 %8, %8, %25;\n\t"
-            "subc.cc.u32 %9, %9, %26;\n\t"
-            "subc.cc.u32 %10, %10, %27;\n\t"
-            "subc.cc.u32 %11, %11, %28;\n\t"
-            "subc.cc.u32 %12, %12, %29;\n\t"
-            "subc.cc.u32 %13, %13, %30;\n\t"
-            "subc.cc.u32 %14, %14, %31;\n\t"
-            "subc.cc.u32 %15, %15, %32;\n\t"
-            "subc.u32 %16, 0, 0;"
-            : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
-              "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15]), "=r"(br)
-            : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
-              "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]));
-        return br;
-    }
-
-    // high half of t += p & mask  (adds p * 2^256 when mask is all ones)
-    static __device__ __forceinline__ void add_p_high(uint32_t* t, uint32_t mask) {
-        uint32_t m0 = P::P0 & mask, m1 = P::P1 & mask, m2 = P::P2 & mask, m3 = P::P3 & mask,
-                 m4 = P::P4 & mask, m5 = P::P5 & mask, m6 = P::P6 & mask, m7 = P::P7 & mask;
-        asm("add.cc.u32 %0, %0, %8;\n\t"
-            "addc.cc.u32 %1, %1, %9;\n\t"
-            "addc.cc.u32 %2, %2, %10;\n\t"
-            "addc.cc.u32 %3, %3, %11;\n\t"
-            "addc.cc.u32 %4, %4, %12;\n\t"
-            "addc.cc.u32 %5, %5, %13;\n\t"
-            "addc.cc.u32 %6, %6, %14;\n\t"
-            "addc.u32 %7, %7, %15;"
-            : "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
-            : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(m6), "r"(m7));
-    }
-
-    // Montgomery reduction of a 512-bit t < p * 2^256: returns (t + M p) / 2^256 reduced once, i.e. in [0, p) when
-    // t < p^2 * 1 (result before the subtraction < t / 2^256 + p < 2p).
-    static __device__ __forceinline__ fe redc(const uint32_t* t) {
+    static __device__ __forceinline__ fe redc_v1(const uint32_t* t) {
         uint32_t x[8], e[8], carry = 0;
         #pragma unroll
         for (int i = 0; i < 8; i++) x[i] = t[i];
@@ -362,8 +562,13 @@ struct Fp {
     // a*b - c*d with ONE Montgomery reduction (two 512-bit products, wide subtraction, + p*2^256 when negative)
     static __device__ __forceinline__ fe mul_sub(const fe& a, const fe& b, const fe& c, const fe& d) {
         uint32_t u[16], v[16];
+#ifdef B2G_FQ_MULSUB_MULWIDE_V1
+        mul_wide_v1(u, a, b);
+        mul_wide_v1(v, c, d);
+#else
         mul_wide(u, a, b);
         mul_wide(v, c, d);
+#endif
         const uint32_t br = sub_wide(u, v);
         add_p_high(u, br);
         return redc(u);
@@ -394,6 +599,16 @@ struct fe2 { fe c0, c1; };
 
 // Fq2 mul / sqr are real calls: inlining them makes the G2 accumulation kernel 13 k instructions (210 KB) and 1.6x slower
 #define B2G_FQ2_CALL __noinline__
+#ifdef B2G_FQ2_MULWIDE_V2
+#define FQ2_MULW Fq::mul_wide
+#else
+#define FQ2_MULW Fq::mul_wide_v1
+#endif
+#ifdef B2G_FQ2_REDC_V1
+#define FQ2_REDC Fq::redc_v1
+#else
+#define FQ2_REDC Fq::redc
+#endif
 
 struct Fq2 {
     using elem = fe2;
@@ -410,14 +625,14 @@ struct Fq2 {
     static __device__ B2G_FQ2_CALL fe2 mul(const fe2& a, const fe2& b) {
         uint32_t v0[16], v1[16], v2[16];
         fe sa = add_noreduce(a.c0, a.c1), sb = add_noreduce(b.c0, b.c1);      // < 2p < 2^255
-        Fq::mul_wide(v0, a.c0, b.c0);
-        Fq::mul_wide(v1, a.c1, b.c1);
-        Fq::mul_wide(v2, sa, sb);
+        FQ2_MULW(v0, a.c0, b.c0);
+        FQ2_MULW(v1, a.c1, b.c1);
+        FQ2_MULW(v2, sa, sb);
         Fq::sub_wide(v2, v0);
         Fq::sub_wide(v2, v1);                                                 // a0 b1 + a1 b0 in [0, 2 p^2)
         const uint32_t br = Fq::sub_wide(v0, v1);                             // a0 b0 - a1 b1 (mod 2^512)
         Fq::add_p_high(v0, br);                                               // + p * 2^256 if negative: now in [0, p^2) or [p R - p^2, p R)
-        fe2 r; r.c0 = Fq::redc(v0); r.c1 = Fq::redc(v2);
+        fe2 r; r.c0 = FQ2_REDC(v0); r.c1 = FQ2_REDC(v2);
         return r;
     }
     static __device__ __forceinline__ fe add_noreduce(const fe& a, const fe& b) {
@@ -435,7 +650,36 @@ struct Fq2 {
               "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
         return s;
     }
-    static __device__ __forceinline__ fe2 mul_sub(const fe2& a, const fe2& b, const fe2& c, const fe2& d) { return sub(mul(a, b), mul(c, d)); }
+    // a*b - c*d with two reductions instead of four: both Karatsuba triples are combined as 512-bit two's-complement
+    // values (|.| < 2 p^2 < 2^509, so bit 511 is the sign), p * 2^256 is added to a negative one, then one redc each.
+    static __device__ B2G_FQ2_CALL fe2 mul_sub(const fe2& a, const fe2& b, const fe2& c, const fe2& d) {
+#ifndef B2G_FQ2_MULSUB_FUSED
+        return sub(mul(a, b), mul(c, d));
+#else
+        uint32_t X[16], Y[16], T[16];
+        {
+            fe sa = add_noreduce(a.c0, a.c1), sb = add_noreduce(b.c0, b.c1);
+            FQ2_MULW(Y, sa, sb);                                          // (a0 + a1)(b0 + b1)
+        }
+        FQ2_MULW(X, a.c0, b.c0);                                          // a0 b0
+        Fq::sub_wide(Y, X);
+        FQ2_MULW(T, a.c1, b.c1);                                          // a1 b1
+        Fq::sub_wide(X, T); Fq::sub_wide(Y, T);
+        FQ2_MULW(T, c.c0, d.c0);                                          // c0 d0
+        Fq::sub_wide(X, T); Fq::add_wide(Y, T);
+        FQ2_MULW(T, c.c1, d.c1);                                          // c1 d1
+        Fq::add_wide(X, T); Fq::add_wide(Y, T);
+        {
+            fe sc = add_noreduce(c.c0, c.c1), sd = add_noreduce(d.c0, d.c1);
+            FQ2_MULW(T, sc, sd);                                          // (c0 + c1)(d0 + d1)
+        }
+        Fq::sub_wide(Y, T);
+        Fq::add_p_high(X, (uint32_t)((int32_t)X[15] >> 31));
+        Fq::add_p_high(Y, (uint32_t)((int32_t)Y[15] >> 31));
+        fe2 r; r.c0 = FQ2_REDC(X); r.c1 = FQ2_REDC(Y);
+        return r;
+#endif
+    }
     static __device__ B2G_FQ2_CALL fe2 sqr(const fe2& a) {
         fe s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
         fe2 r; r.c0 = Fq::mul(s, d); r.c1 = Fq::dbl(m);

@@ -47,8 +47,9 @@ inline int msm_pick_c(uint32_t n) {
     int lg = 0; while ((1ull << (lg + 1)) <= n) lg++;
     int c = lg - 3;
     if (c < 8) c = 8;
-    if (c > 16) c = 16;                  // B2G_MSM_C overrides (8..22) for tuning
-    return c;
+    if (c > 16) c = 16;
+    if (n >= 3u << 18) c = 17;           // 15 windows instead of 16 pay for the doubled bucket set from ~0.8 M bases up (measured;
+    return c;                            // 18 already loses to the bucket reduction).  B2G_MSM_C overrides (8..22) for tuning
 }
 inline int msm_nwin(int c) { return (255 + c - 1) / c; }
 

@@ -322,6 +322,20 @@ __global__ void test_op_kernel(int op, const uint8_t* __restrict__ a, const uint
         G2::Pt acc = G2::from_affine(aff_load<Fq2>(a, i));
         G2::madd(acc, aff_load<Fq2>(b, i));
         aff_store<Fq2>(out, i, G2::to_affine(acc));
+    } else if (op <= 16) {      // the lazy-reduction blocks on raw Montgomery residues
+        fe x = fe_load(a + 32 * (size_t)i), y = fe_load(b + 32 * (size_t)i), r;
+        if (op == 14) r = Fq::sqr(x);
+        else if (op == 15) r = Fq::mul_sub(x, y, y, y);
+        else { uint32_t t[16]; Fq::mul_wide(t, x, y); r = Fq::redc(t); }
+        fe_store(out + 32 * (size_t)i, r);
+    } else {                    // 17 fq2_mul, 18 fq2_sqr, 19 fq2_mul_sub(a, b, b, swap(a))
+        fe2 x, y, r;
+        x.c0 = fe_load(a + 64 * (size_t)i); x.c1 = fe_load(a + 64 * (size_t)i + 32);
+        y.c0 = fe_load(b + 64 * (size_t)i); y.c1 = fe_load(b + 64 * (size_t)i + 32);
+        if (op == 17) r = Fq2::mul(x, y);
+        else if (op == 18) r = Fq2::sqr(x);
+        else { fe2 z; z.c0 = x.c1; z.c1 = x.c0; r = Fq2::mul_sub(x, y, y, z); }
+        fe_store(out + 64 * (size_t)i, r.c0); fe_store(out + 64 * (size_t)i + 32, r.c1);
     }
 }
 
@@ -947,11 +961,11 @@ int b2g_fixed_base_g2(b2g_ctx* ctx, const void* scalars_canon, size_t n, void* o
 
 int b2g_test_op(b2g_ctx* ctx, int op, const void* a, const void* b, size_t n, void* out) {
     return guarded([&] {
-        if (!ctx || !a || !out || op < 0 || op > 13) throw_error(B2G_E_SHAPE, "bad arguments");
+        if (!ctx || !a || !out || op < 0 || op > 19) throw_error(B2G_E_SHAPE, "bad arguments");
         if (n == 0) return;
         DevGuard g(ctx->device);
         cudaStream_t st = ctx->st[0];
-        const size_t esz = op <= 7 ? 32 : ((op == 9 || op == 11 || op == 13) ? 128 : 64);
+        const size_t esz = (op <= 7 || (op >= 14 && op <= 16)) ? 32 : ((op == 9 || op == 11 || op == 13) ? 128 : 64);
         uint8_t* da = dev_upload<uint8_t>(a, n * esz, st);
         uint8_t* db = dev_upload<uint8_t>(b ? b : a, n * esz, st);
         uint8_t* dout = nullptr; CUDA_CHECK(cudaMalloc(&dout, n * esz));

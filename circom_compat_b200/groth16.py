@@ -172,7 +172,7 @@ class Context:
 
     def test_op(self, op: int, a, b=None) -> np.ndarray:
         a = _c(a); b = _c(b) if b is not None else None
-        words = 4 if op <= 7 else (16 if op in (9, 11, 13) else 8)
+        words = 4 if (op <= 7 or 14 <= op <= 16) else (16 if op in (9, 11, 13) else 8)
         n = a.size // words
         out = np.zeros_like(a)
         N.check(N.lib().b2g_test_op(self._h, op, _ptr(a), _ptr(b) if b is not None else None, n, _ptr(out)))

@@ -155,7 +155,9 @@ B2G_API int b2g_fixed_base_g2(b2g_ctx* ctx, const void* scalars_canon, size_t n,
 
 /* Element-wise device arithmetic, for unit parity tests of the field / group layers.
  * op: 0 fq_mul, 1 fq_add, 2 fq_sub, 3 fr_mul, 4 fr_add, 5 fr_sub, 6 fq_inv, 7 fr_inv (b ignored),
- *     8 g1_add (a, b, out = n x 64 B affine), 9 g2_add (n x 128 B), 10 g1_dbl, 11 g2_dbl (b ignored). */
+ *     8 g1_add (a, b, out = n x 64 B affine), 9 g2_add (n x 128 B), 10 g1_dbl, 11 g2_dbl (b ignored),
+ *     12 g1 mixed add, 13 g2 mixed add, 14 fq_sqr, 15 fq a*b - b*b, 16 fq mul through the lazy-reduction blocks (32 B),
+ *     17 fq2_mul, 18 fq2_sqr, 19 fq2 a*b - b*swap(a) (n x 64 B: c0 || c1). */
 B2G_API int b2g_test_op(b2g_ctx* ctx, int op, const void* a, const void* b, size_t n, void* out);
 
 /* Timing of the last b2g_prove / b2g_prove_partial on this ctx, CUDA-event milliseconds:

@@ -38,6 +38,49 @@ def test_field_ops(ctx, field):
     assert c.limbs_to_ints(from_m(inv)) == [pow(x, -1, mod) for x in nz]
 
 
+def _raw_residues(rng, n, mod):
+    """Raw Montgomery residues (any integer < mod) with extreme limb patterns mixed in."""
+    pat = [0, 1, 0xffffffff, 0xfffffffe, 0x80000000, 0x7fffffff]
+    out = [0, 1, mod - 1, mod - 2, mod >> 1, (1 << 253) - 1, 1 << 253]
+    while len(out) < n:
+        if rng.random() < 0.5:
+            out.append(rng.randrange(mod))
+        else:
+            v = sum(rng.choice(pat + [rng.getrandbits(32)]) << (32 * i) for i in range(8)) % mod
+            out.append(v)
+    return out[:n]
+
+
+def test_lazy_reduction_blocks(ctx):
+    """sqr / mul_wide / redc / mul_sub and the Fq2 routines built on them, on raw residues: out = x*y*R^-1 mod q."""
+    rng = random.Random(77)
+    q = o.Q_MOD
+    rinv = pow(1 << 256, -1, q)
+    n = 4000
+    x, y = _raw_residues(rng, n, q), _raw_residues(rng, n, q)[::-1]
+    xl, yl = c.ints_to_limbs(x), c.ints_to_limbs(y)
+    assert c.limbs_to_ints(ctx.test_op(14, xl, yl)) == [a * a * rinv % q for a in x]
+    assert c.limbs_to_ints(ctx.test_op(15, xl, yl)) == [(a * b - b * b) * rinv % q for a, b in zip(x, y)]
+    assert c.limbs_to_ints(ctx.test_op(16, xl, yl)) == [a * b * rinv % q for a, b in zip(x, y)]
+    assert c.limbs_to_ints(ctx.test_op(0, xl, yl)) == [a * b * rinv % q for a, b in zip(x, y)]
+    # Fq2 = Fq[u]/(u^2+1): elements are consecutive pairs
+    x2 = list(zip(x[0::2], x[1::2])); y2 = list(zip(y[0::2], y[1::2]))
+
+    def mul2(a, b):
+        return ((a[0] * b[0] - a[1] * b[1]) * rinv % q, (a[0] * b[1] + a[1] * b[0]) * rinv % q)
+
+    def flat(v):
+        return [t for pair in v for t in pair]
+
+    assert c.limbs_to_ints(ctx.test_op(17, xl, yl)) == flat([mul2(a, b) for a, b in zip(x2, y2)])
+    assert c.limbs_to_ints(ctx.test_op(18, xl, yl)) == flat([mul2(a, a) for a in x2])
+    exp = []
+    for a, b in zip(x2, y2):
+        p1, p2 = mul2(a, b), mul2(b, (a[1], a[0]))
+        exp.append(((p1[0] - p2[0]) % q, (p1[1] - p2[1]) % q))
+    assert c.limbs_to_ints(ctx.test_op(19, xl, yl)) == flat(exp)
+
+
 def test_group_ops(ctx):
     rng = random.Random(5)
     n = 200
