@@ -241,13 +241,9 @@ struct Fp {
     }
     // defined after the lazy-reduction blocks: sqr(a) = redc(sqr_wide(a)), 36 + 64 products instead of 128
     static __device__ __forceinline__ fe sqr(const fe& a) {
-#ifdef B2G_SQR_IS_MUL
-        return mul(a, a);
-#else
         uint32_t t[16];
         sqr_wide(t, a);
         return redc(t);
-#endif
     }
 
     // ------------------------------------------------------------------ lazy-reduction building blocks (used by Fq2)
@@ -391,30 +387,6 @@ struct Fp {
         return br;
     }
 
-    // t += u  (512-bit, carry out discarded)
-    static __device__ __forceinline__ void add_wide(uint32_t* t, const uint32_t* u) {
-        asm("add.cc.u32 %0, %0, %16;\n\t"
-            "addc.cc.u32 %1, %1, %17;\n\t"
-            "addc.cc.u32 %2, %2, %18;\n\t"
-            "addc.cc.u32 %3, %3, %19;\n\t"
-            "addc.cc.u32 %4, %4, %20;\n\t"
-            "addc.cc.u32 %5, %5, %21;\n\t"
-            "addc.cc.u32 %6, %6, %22;\n\t"
-            "addc.cc.u32 %7, %7, %23;\n\t"
-            "addc.cc.u32 %8, %8, %24;\n\t"
-            "addc.cc.u32 %9, %9, %25;\n\t"
-            "addc.cc.u32 %10, %10, %26;\n\t"
-            "addc.cc.u32 %11, %11, %27;\n\t"
-            "addc.cc.u32 %12, %12, %28;\n\t"
-            "addc.cc.u32 %13, %13, %29;\n\t"
-            "addc.cc.u32 %14, %14, %30;\n\t"
-            "addc.u32 %15, %15, %31;"
-            : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]),
-              "+r"(t[8]), "+r"(t[9]), "+r"(t[10]), "+r"(t[11]), "+r"(t[12]), "+r"(t[13]), "+r"(t[14]), "+r"(t[15])
-            : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
-              "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]));
-    }
-
     // high half of t += p & mask  (adds p * 2^256 when mask is all ones)
     static __device__ __forceinline__ void add_p_high(uint32_t* t, uint32_t mask) {
         uint32_t m0 = P::P0 & mask, m1 = P::P1 & mask, m2 = P::P2 & mask, m3 = P::P3 & mask,
@@ -488,8 +460,10 @@ struct Fp {
         return reduce_once(r);
     }
 
-    // ---- first-generation forms (independent column chains / per-row shift adds): more ALU work, more ILP
-    static __device__ __forceinline__ void mul_wide_v1(uint32_t* t, const fe& a, const fe& b) {
+    // Column form of the same product: sixteen independent 8-limb chains on zero-initialised even/odd accumulators.  More
+    // ALU instructions than mul_wide() but no row-to-row dependency; the Fq2 routines, which run at 3 warps per scheduler
+    // inside the G2 accumulation kernel and live off instruction-level parallelism, are 4 % faster with it (measured).
+    static __device__ __forceinline__ void mul_wide_cols(uint32_t* t, const fe& a, const fe& b) {
         uint32_t ev[17], od[16];
         #pragma unroll
         for (int i = 0; i < 17; i++) ev[i] = 0;
@@ -529,46 +503,11 @@ struct Fp {
               "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
     }
 
-    static __device__ __forceinline__ fe redc_v1(const uint32_t* t) {
-        uint32_t x[8], e[8], carry = 0;
-        #pragma unroll
-        for (int i = 0; i < 8; i++) x[i] = t[i];
-        #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t m = x[0] * P::INV;
-            mul4(e, P::P1, P::P3, P::P5, P::P7, m);                 // positions 1..8
-            e[7] += carry;                                          // carry of the previous shift (position 8 -> 7 after it)
-            cmad4(x, e[7], P::P0, P::P2, P::P4, P::P6, m);          // x[0] becomes 0
-            // shift right by one limb: x'[k] = e[k] + x[k+1], x'[7] = e[7] + t[8+i]; carry -> next row
-            asm("add.cc.u32 %0, %9, %17;\n\t"
-                "addc.cc.u32 %1, %10, %18;\n\t"
-                "addc.cc.u32 %2, %11, %19;\n\t"
-                "addc.cc.u32 %3, %12, %20;\n\t"
-                "addc.cc.u32 %4, %13, %21;\n\t"
-                "addc.cc.u32 %5, %14, %22;\n\t"
-                "addc.cc.u32 %6, %15, %23;\n\t"
-                "addc.cc.u32 %7, %16, %24;\n\t"
-                "addc.u32 %8, 0, 0;"
-                : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7]), "=r"(carry)
-                : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
-                  "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]), "r"(t[8 + i]));
-        }
-        fe r;
-        #pragma unroll
-        for (int i = 0; i < 8; i++) r.l[i] = x[i];
-        return reduce_once(r);                                      // carry is 0 here: the value is < 2p < 2^255
-    }
-
     // a*b - c*d with ONE Montgomery reduction (two 512-bit products, wide subtraction, + p*2^256 when negative)
     static __device__ __forceinline__ fe mul_sub(const fe& a, const fe& b, const fe& c, const fe& d) {
         uint32_t u[16], v[16];
-#ifdef B2G_FQ_MULSUB_MULWIDE_V1
-        mul_wide_v1(u, a, b);
-        mul_wide_v1(v, c, d);
-#else
         mul_wide(u, a, b);
         mul_wide(v, c, d);
-#endif
         const uint32_t br = sub_wide(u, v);
         add_p_high(u, br);
         return redc(u);
@@ -599,17 +538,6 @@ struct fe2 { fe c0, c1; };
 
 // Fq2 mul / sqr are real calls: inlining them makes the G2 accumulation kernel 13 k instructions (210 KB) and 1.6x slower
 #define B2G_FQ2_CALL __noinline__
-#ifdef B2G_FQ2_MULWIDE_V2
-#define FQ2_MULW Fq::mul_wide
-#else
-#define FQ2_MULW Fq::mul_wide_v1
-#endif
-#ifdef B2G_FQ2_REDC_V1
-#define FQ2_REDC Fq::redc_v1
-#else
-#define FQ2_REDC Fq::redc
-#endif
-
 struct Fq2 {
     using elem = fe2;
     static __device__ __forceinline__ fe2 zero() { fe2 r; r.c0 = fe_zero(); r.c1 = fe_zero(); return r; }
@@ -625,14 +553,14 @@ struct Fq2 {
     static __device__ B2G_FQ2_CALL fe2 mul(const fe2& a, const fe2& b) {
         uint32_t v0[16], v1[16], v2[16];
         fe sa = add_noreduce(a.c0, a.c1), sb = add_noreduce(b.c0, b.c1);      // < 2p < 2^255
-        FQ2_MULW(v0, a.c0, b.c0);
-        FQ2_MULW(v1, a.c1, b.c1);
-        FQ2_MULW(v2, sa, sb);
+        Fq::mul_wide_cols(v0, a.c0, b.c0);
+        Fq::mul_wide_cols(v1, a.c1, b.c1);
+        Fq::mul_wide_cols(v2, sa, sb);
         Fq::sub_wide(v2, v0);
         Fq::sub_wide(v2, v1);                                                 // a0 b1 + a1 b0 in [0, 2 p^2)
         const uint32_t br = Fq::sub_wide(v0, v1);                             // a0 b0 - a1 b1 (mod 2^512)
         Fq::add_p_high(v0, br);                                               // + p * 2^256 if negative: now in [0, p^2) or [p R - p^2, p R)
-        fe2 r; r.c0 = FQ2_REDC(v0); r.c1 = FQ2_REDC(v2);
+        fe2 r; r.c0 = Fq::redc(v0); r.c1 = Fq::redc(v2);
         return r;
     }
     static __device__ __forceinline__ fe add_noreduce(const fe& a, const fe& b) {
@@ -650,36 +578,10 @@ struct Fq2 {
               "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
         return s;
     }
-    // a*b - c*d with two reductions instead of four: both Karatsuba triples are combined as 512-bit two's-complement
-    // values (|.| < 2 p^2 < 2^509, so bit 511 is the sign), p * 2^256 is added to a negative one, then one redc each.
-    static __device__ B2G_FQ2_CALL fe2 mul_sub(const fe2& a, const fe2& b, const fe2& c, const fe2& d) {
-#ifndef B2G_FQ2_MULSUB_FUSED
-        return sub(mul(a, b), mul(c, d));
-#else
-        uint32_t X[16], Y[16], T[16];
-        {
-            fe sa = add_noreduce(a.c0, a.c1), sb = add_noreduce(b.c0, b.c1);
-            FQ2_MULW(Y, sa, sb);                                          // (a0 + a1)(b0 + b1)
-        }
-        FQ2_MULW(X, a.c0, b.c0);                                          // a0 b0
-        Fq::sub_wide(Y, X);
-        FQ2_MULW(T, a.c1, b.c1);                                          // a1 b1
-        Fq::sub_wide(X, T); Fq::sub_wide(Y, T);
-        FQ2_MULW(T, c.c0, d.c0);                                          // c0 d0
-        Fq::sub_wide(X, T); Fq::add_wide(Y, T);
-        FQ2_MULW(T, c.c1, d.c1);                                          // c1 d1
-        Fq::add_wide(X, T); Fq::add_wide(Y, T);
-        {
-            fe sc = add_noreduce(c.c0, c.c1), sd = add_noreduce(d.c0, d.c1);
-            FQ2_MULW(T, sc, sd);                                          // (c0 + c1)(d0 + d1)
-        }
-        Fq::sub_wide(Y, T);
-        Fq::add_p_high(X, (uint32_t)((int32_t)X[15] >> 31));
-        Fq::add_p_high(Y, (uint32_t)((int32_t)Y[15] >> 31));
-        fe2 r; r.c0 = FQ2_REDC(X); r.c1 = FQ2_REDC(Y);
-        return r;
-#endif
-    }
+    // (a fused a*b - c*d with six wide products and two reductions was measured 3 - 8 % SLOWER inside the G2 kernel:
+    // fewer IMAD.WIDE but one long dependent chain; the kernel is latency-, not issue-bound at 3 warps per scheduler)
+    // a real call like mul/sqr (that is the build that was measured)
+    static __device__ B2G_FQ2_CALL fe2 mul_sub(const fe2& a, const fe2& b, const fe2& c, const fe2& d) { return sub(mul(a, b), mul(c, d)); }
     static __device__ B2G_FQ2_CALL fe2 sqr(const fe2& a) {
         fe s = Fq::add(a.c0, a.c1), d = Fq::sub(a.c0, a.c1), m = Fq::mul(a.c0, a.c1);
         fe2 r; r.c0 = Fq::mul(s, d); r.c1 = Fq::dbl(m);
