@@ -1,0 +1,197 @@
+// dfma_probe.cu - ROUND-2 CANDIDATE harness (standalone; not part of the product, its tests or its bench).
+//   1. checks fp52 mont_mul / mont_sqr (FP64 pipe) against Fp<FqParams>::mul (IMAD pipe) on random residues, on the GPU;
+//   2. measures field multiplications per second for: all warps integer, all warps FP64, and warps alternating between the
+//      two (the question that decides whether a mixed accumulation kernel is worth building: do the pipes overlap?).
+// Build: make -C experiments/dfma ; run on a B200: experiments/dfma/dfma_probe [n_threads_log2=20] [iters=2000]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../circom_compat_b200/csrc/fp.cuh"
+#include "../../circom_compat_b200/csrc/ec.cuh"
+#include "accumulate52.cuh"
+
+using namespace b2g;
+using b2g52::fe52;
+
+__device__ fe52 to52(const fe& x) { return b2g52::from_u32(x.l); }
+// five signed limbs with |value| < 2 p  ->  canonical residue in [0, p)
+__device__ void reduce3(uint32_t* w) {
+    fe r;
+    for (int i = 0; i < 8; i++) r.l[i] = w[i];
+    r = Fq::reduce_once(r); r = Fq::reduce_once(r); r = Fq::reduce_once(r);
+    for (int i = 0; i < 8; i++) w[i] = r.l[i];
+}
+__device__ fe from52(const fe52& a) {
+    fe r;
+    b2g52::to_u32_plus_2p(a, r.l);
+    reduce3(r.l);
+    return r;
+}
+
+using G1c = Curve<Fq>;
+
+// thread i: points P_k = [(i * 8 + k) * 2654435761 + 1] G (affine, product representation), k < 8, alternating signs;
+// integer path: G1 XYZZ madd chain; FP64 path: madd52 chain + store52.  out[8 i ..] = X, Y, ZZ, ZZZ of both.
+__global__ void ec_check_kernel(fe* __restrict__ out, uint32_t n, uint32_t* __restrict__ redo_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1c::Aff g; g.x = Fq::one(); g.y = Fq::dbl(Fq::one());                   // generator (1, 2)
+    G1c::Pt acc = G1c::infinity();
+    b2g52::Pt52 acc52; bool first = true, ok = true;
+    for (int k = 0; k < 8; k++) {
+        fe sc = fe_zero(); sc.l[0] = (i * 8u + k) * 2654435761u + 1u; sc.l[1] = i ^ (0x9e3779b9u * k);
+        G1c::Aff p = G1c::to_affine(G1c::mul_scalar(G1c::from_affine(g), sc.l));
+        if (k & 1) p.y = Fq::neg(p.y);
+        G1c::madd(acc, p);
+        fe52 x2 = to52(p.x), y2 = to52(p.y);
+        if (first) { b2g52::from_affine52(acc52, x2, y2); first = false; }
+        else ok = ok && b2g52::madd52(acc52, x2, y2);
+    }
+    if (!ok) atomicAdd(redo_count, 1u);
+    out[8 * i + 0] = acc.x; out[8 * i + 1] = acc.y; out[8 * i + 2] = acc.zz; out[8 * i + 3] = acc.zzz;
+    uint32_t w[32];
+    b2g52::store52(acc52, w, reduce3);
+    for (int c = 0; c < 4; c++) { fe r; for (int j = 0; j < 8; j++) r.l[j] = w[8 * c + j]; out[8 * i + 4 + c] = r; }
+}
+
+// compile check of the accumulation kernel (launched by round 2's integration, not by this probe)
+__global__ void __launch_bounds__(128, 4) msm_accumulate52_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
+                                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk, void* __restrict__ buckets,
+                                      void* __restrict__ frag_first, void* __restrict__ frag_last, uint32_t t_begin, uint32_t t_end,
+                                      uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count) {
+    const uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_end) return;
+    b2g52::accumulate52_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
+                            [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
+}
+
+// madd throughput: every thread walks `iters` times over 32 affine points that sit in global memory (L2-resident), as the
+// accumulation kernel does with table rows.  mode as in probe_kernel.
+__global__ void __launch_bounds__(128) madd_probe_kernel(int mode, int iters, const fe* __restrict__ pts, fe* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool use_fp64 = mode == 1 || (mode == 2 && ((threadIdx.x >> 5) & 1));
+    const fe* my = pts + 2 * (size_t)((i * 37u) & 1023u);
+    if (!use_fp64) {
+        G1c::Pt acc = G1c::infinity();
+        #pragma unroll 1
+        for (int k = 0; k < iters; k++) {
+            G1c::Aff p; p.x = fe_load_nc(my + 2 * (k & 31)); p.y = fe_load_nc(my + 2 * (k & 31) + 1);
+            G1c::madd(acc, p);
+        }
+        out[i] = Fq::add(acc.x, acc.zz);
+    } else {
+        b2g52::Pt52 acc;
+        { fe x = fe_load_nc(my), y = fe_load_nc(my + 1); b2g52::from_affine52(acc, to52(x), to52(y)); }
+        bool ok = true;
+        #pragma unroll 1
+        for (int k = 1; k < iters; k++) {
+            fe x = fe_load_nc(my + 2 * (k & 31)), y = fe_load_nc(my + 2 * (k & 31) + 1);
+            ok = b2g52::madd52(acc, to52(x), to52(y)) && ok;
+        }
+        fe r = from52(b2g52::add(acc.X, acc.ZZ));
+        if (!ok) r.l[0] ^= 1u;
+        out[i] = r;
+    }
+}
+
+// out[3 i + 0] = x * y * 2^-256 (integer path), out[3 i + 1] = 16 * (x * y * 2^-260) (FP64 path), out[3 i + 2] = same for x^2
+__global__ void check_kernel(const fe* __restrict__ in, fe* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = in[2 * i], y = in[2 * i + 1];
+    out[4 * i + 0] = Fq::mul(x, y);
+    out[4 * i + 2] = Fq::mul(x, x);
+    fe52 a = to52(x), b = to52(y);
+    fe r = from52(b2g52::mont_mul(a, b));
+    for (int k = 0; k < 4; k++) r = Fq::dbl(r);
+    out[4 * i + 1] = r;
+    fe s = from52(b2g52::mont_sqr(a));
+    for (int k = 0; k < 4; k++) s = Fq::dbl(s);
+    out[4 * i + 3] = s;
+}
+
+// mode 0: every warp on the integer pipe; 1: every warp on the FP64 pipe; 2: even warps integer, odd warps FP64.
+// Two independent dependency chains per thread, `iters` products on each.
+__global__ void __launch_bounds__(128) probe_kernel(int mode, int iters, const fe* __restrict__ in, fe* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool use_fp64 = mode == 1 || (mode == 2 && ((threadIdx.x >> 5) & 1));
+    fe x = in[2 * i], y = in[2 * i + 1];
+    if (!use_fp64) {
+        fe u = x, v = y;
+        #pragma unroll 1
+        for (int k = 0; k < iters; k++) { u = Fq::mul(u, y); v = Fq::mul(v, x); }
+        out[i] = Fq::add(u, v);
+    } else {
+        fe52 a = to52(x), b = to52(y), u = a, v = b;
+        #pragma unroll 1
+        for (int k = 0; k < iters; k++) { u = b2g52::mont_mul(u, b); v = b2g52::mont_mul(v, a); }
+        out[i] = from52(b2g52::normalize(b2g52::add(u, v)));
+    }
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+int main(int argc, char** argv) {
+    const int logn = argc > 1 ? atoi(argv[1]) : 20, iters = argc > 2 ? atoi(argv[2]) : 2000;
+    const uint32_t n = 1u << logn;
+    std::vector<uint32_t> h((size_t)n * 16);
+    uint64_t s = 0x9e3779b97f4a7c15ull;
+    for (auto& w : h) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; w = (uint32_t)(s >> 16); }
+    for (size_t e = 0; e < (size_t)n * 2; e++) h[e * 8 + 7] &= 0x1fffffffu;      // < 2^253 < p
+    fe *d_in, *d_out;
+    CK(cudaMalloc(&d_in, (size_t)n * 64)); CK(cudaMalloc(&d_out, (size_t)n * 128));
+    CK(cudaMemcpy(d_in, h.data(), (size_t)n * 64, cudaMemcpyHostToDevice));
+    // 1. parity of the two multipliers
+    const uint32_t nc = n < 65536 ? n : 65536;
+    check_kernel<<<(nc + 127) / 128, 128>>>(d_in, d_out, nc);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> o((size_t)nc * 32);
+    CK(cudaMemcpy(o.data(), d_out, (size_t)nc * 128, cudaMemcpyDeviceToHost));
+    size_t bad = 0;
+    for (uint32_t i = 0; i < nc; i++)
+        bad += (memcmp(&o[(size_t)i * 32], &o[(size_t)i * 32 + 8], 32) != 0) + (memcmp(&o[(size_t)i * 32 + 16], &o[(size_t)i * 32 + 24], 32) != 0);
+    printf("{\"check\": {\"pairs\": %u, \"mismatches\": %zu}}\n", nc, bad);
+    // 1b. parity of the two mixed additions
+    {
+        const uint32_t ne = 8192;
+        uint32_t* d_redo; CK(cudaMalloc(&d_redo, 4)); CK(cudaMemset(d_redo, 0, 4));
+        ec_check_kernel<<<ne / 64, 64>>>(d_out, ne, d_redo);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> e((size_t)ne * 64); uint32_t redo = 0;
+        CK(cudaMemcpy(e.data(), d_out, (size_t)ne * 256, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&redo, d_redo, 4, cudaMemcpyDeviceToHost));
+        size_t ebad = 0;
+        for (uint32_t i = 0; i < ne; i++) ebad += memcmp(&e[(size_t)i * 64], &e[(size_t)i * 64 + 32], 128) != 0;
+        printf("{\"ec_check\": {\"chains\": %u, \"mismatches\": %zu, \"redo_flags\": %u}}\n", ne, ebad, redo);
+        bad += ebad;
+        // points for the madd probe: reuse the affine points implied by the first 2048 outputs?  simpler: X, Y of the integer
+        // results are not affine; build 1024 affine points = first 1024 (x, y) pairs of a fixed-base walk on the host side is
+        // overkill - take the check kernel's inputs instead: d_in holds residues < p that are not curve points, which is fine
+        // for timing (no exceptional case can trigger: the formulas never test curve membership).
+    }
+    // 2. throughput
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int mode = 0; mode < 3; mode++) {
+        probe_kernel<<<n / 128, 128>>>(mode, 16, d_in, d_out);                  // warm-up
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        probe_kernel<<<n / 128, 128>>>(mode, iters, d_in, d_out);
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double muls = 2.0 * iters * n;
+        printf("{\"mode\": %d, \"what\": \"%s\", \"ms\": %.3f, \"field_muls_per_s\": %.4g}\n", mode,
+               mode == 0 ? "all warps IMAD" : mode == 1 ? "all warps DFMA" : "even warps IMAD, odd warps DFMA", ms, muls / (ms * 1e-3));
+    }
+    for (int mode = 0; mode < 3; mode++) {
+        const int it = iters / 8 > 32 ? iters / 8 : 32;
+        madd_probe_kernel<<<n / 128, 128>>>(mode, 32, d_in, d_out);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        madd_probe_kernel<<<n / 128, 128>>>(mode, it, d_in, d_out);
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("{\"madd_mode\": %d, \"what\": \"%s\", \"ms\": %.3f, \"mixed_adds_per_s\": %.4g}\n", mode,
+               mode == 0 ? "all warps IMAD" : mode == 1 ? "all warps DFMA" : "even warps IMAD, odd warps DFMA", ms, (double)it * n / (ms * 1e-3));
+    }
+    return bad ? 2 : 0;
+}
