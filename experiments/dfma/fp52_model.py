@@ -188,23 +188,34 @@ def column_low(t):
     return fadd(from_raw(l + RAW_B), -from_raw(RAW_B)), c
 
 
-def mont_mul_gpu(a, b, square=False):
+def split_sub(a, b, T, lo_k, hi_k):
+    assert -(1 << 103) <= int(a) * int(b) <= (1 << 103)
+    hf = fma_rd(a, b, M)
+    lo = fma(a, b, fadd(MK, -hf))
+    T[hi_k] = (T[hi_k] - raw(hf)) & MASK64
+    T[lo_k] = (T[lo_k] - raw(lo)) & MASK64
+
+
+def mont_core_gpu(mode, a, b, c=None, d=None):
+    """mirror of mont_core<MODE>: 0 a*b, 1 a*a, 2 a*b - c*d"""
     T = []
     for k in range(10):
         nlo = nhi = 0
         for i in range(5):
             for j in range(5):
-                in_prod = (not square) or j >= i
+                in_prod = mode == 0 or (mode == 1 and j >= i)
                 nlo += (in_prod and i + j == k) + (i + j == k)
                 nhi += (in_prod and i + j + 1 == k) + (i + j + 1 == k)
         T.append((-(nlo * RAW_L + nhi * RAW_H)) & MASK64)
     for i in range(5):
-        if square:
+        if mode == 1:
             split_acc(a[i], a[i], T, 2 * i, 2 * i + 1)
             a2 = fadd(a[i], a[i])
             for j in range(i + 1, 5): split_acc(a2, a[j], T, i + j, i + j + 1)
         else:
-            for j in range(5): split_acc(a[i], b[j], T, i + j, i + j + 1)
+            for j in range(5):
+                split_acc(a[i], b[j], T, i + j, i + j + 1)
+                if mode == 2: split_sub(c[i], d[j], T, i + j, i + j + 1)
     for i in range(5):
         l, _ = column_low(T[i] + RAW_L)
         q = split_low(l, PINV_B)
@@ -213,10 +224,14 @@ def mont_mul_gpu(a, b, square=False):
         T[i + 1] = (T[i + 1] + (s64(T[i]) >> 52)) & MASK64
     r = []
     for k in range(5, 9):
-        l, c = column_low(T[k]); T[k + 1] = (T[k + 1] + c) & MASK64; r.append(l)
+        l, c_ = column_low(T[k]); T[k + 1] = (T[k + 1] + c_) & MASK64; r.append(l)
     t9 = s64(T[9]); assert abs(t9) < 1 << 51
     r.append(fadd(from_raw(t9 + RAW_B), -from_raw(RAW_B)))
     return r
+
+
+def mont_mul_gpu(a, b, square=False):
+    return mont_core_gpu(1 if square else 0, a, b)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -255,26 +270,37 @@ class Acc52:
     def __init__(self): self.inf = True; self.redo = False; self.X = self.Y = self.ZZ = self.ZZZ = None
 
 
+class _Impl:
+    """the two restatements of the field layer: 'rn' (balanced halves, big-int columns) and 'gpu' (mirror of fp52.cuh)"""
+    def __init__(self, gpu):
+        self.mul = (lambda a, b: mont_core_gpu(0, a, b)) if gpu else mont_mul
+        self.sqr = (lambda a: mont_core_gpu(1, a, a)) if gpu else mont_sqr
+        self.mul_sub = (lambda a, b, c, d: mont_core_gpu(2, a, b, c, d)) if gpu else mul_sub_fused
+
+
+IMPL = _Impl(False)
+
+
 def madd52(acc, xt, yt, negate=False):
     """acc += (x, y) given as residues xt = x * 2^256 mod p, yt likewise (0, 0 = infinity); negate: add (x, -y)"""
     if xt == 0 and yt == 0: return
     x2, y2 = balanced(xt), balanced(yt)
     if negate: y2 = [-v for v in y2]
     if acc.inf:
-        acc.X, acc.Y = mont_mul(x2, K264), mont_mul(y2, K264)
+        acc.X, acc.Y = IMPL.mul(x2, K264), IMPL.mul(y2, K264)
         acc.ZZ, acc.ZZZ = list(K264), list(K264)
         acc.inf = False
         return
-    U2, S2 = mont_mul(x2, acc.ZZ), mont_mul(y2, acc.ZZZ)
+    U2, S2 = IMPL.mul(x2, acc.ZZ), IMPL.mul(y2, acc.ZZZ)
     Pn, Rn = normalize(lsub(U2, acc.X)), normalize(lsub(S2, acc.Y))
     if abs(Pn[0]) in CAND:                      # necessary for P = 0 mod p: hand the whole run to the integer kernel
         acc.redo = True
         return
-    PP = mont_sqr(Pn); PPP = mont_mul(Pn, PP); Q = mont_mul(acc.X, PP)
-    RR = mont_sqr(Rn)
+    PP = IMPL.sqr(Pn); PPP = IMPL.mul(Pn, PP); Q = IMPL.mul(acc.X, PP)
+    RR = IMPL.sqr(Rn)
     X3 = normalize(lsub(lsub(RR, PPP), ladd(Q, Q)))
-    Y3 = mul_sub_fused(Rn, lsub(Q, X3), acc.Y, PPP)
-    acc.ZZ, acc.ZZZ = mont_mul(acc.ZZ, PP), mont_mul(acc.ZZZ, PPP)
+    Y3 = IMPL.mul_sub(Rn, lsub(Q, X3), acc.Y, PPP)
+    acc.ZZ, acc.ZZZ = IMPL.mul(acc.ZZ, PP), IMPL.mul(acc.ZZZ, PPP)
     acc.X, acc.Y = X3, Y3
     for v, bound in ((acc.X, 2.2), (acc.Y, 1.2), (acc.ZZ, 0.6), (acc.ZZZ, 0.6)):
         assert abs(value(v)) < bound * P
@@ -283,7 +309,7 @@ def madd52(acc, xt, yt, negate=False):
 def store52(acc):
     """-> (X, Y, ZZ, ZZZ) as canonical residues in the product's 2^256 Montgomery form"""
     c = lambda v: value(v) % P
-    return (c(mont_mul(acc.X, K256)), c(mont_mul(acc.Y, K256)), c(mont_mul(acc.ZZ, K252)), c(mont_mul(acc.ZZZ, K252)))
+    return (c(IMPL.mul(acc.X, K256)), c(IMPL.mul(acc.Y, K256)), c(IMPL.mul(acc.ZZ, K252)), c(IMPL.mul(acc.ZZZ, K252)))
 
 
 def _ec_check():
@@ -320,7 +346,55 @@ def _ec_check():
     assert acc.redo
     acc = Acc52(); madd52(acc, x * R256 % P, y * R256 % P); madd52(acc, x * R256 % P, y * R256 % P, True)
     assert acc.redo
-    print("ec52 model ok")
+    print("ec52 model ok (%s field layer)" % ("fp52.cuh mirror" if IMPL.mul is not mont_mul else "round-to-nearest"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mirrors of from_u32 / to_u32_plus_2p (fp52.cuh): 8 x u32 <-> five balanced limbs through 64-bit shifts
+def from_u32_gpu(words):
+    w = [words[2 * i] | (words[2 * i + 1] << 32) for i in range(4)]
+    mask = (1 << 52) - 1
+    chunk = [w[0] & mask, ((w[0] >> 52) | (w[1] << 12)) & mask, ((w[1] >> 40) | (w[2] << 24)) & mask,
+             ((w[2] >> 28) | (w[3] << 36)) & mask, w[3] >> 16]
+    out, carry = [], 0
+    for i in range(4):
+        t = chunk[i] + carry
+        carry = (t + (1 << 51)) >> 52
+        t -= carry << 52
+        out.append(fadd(from_raw(t + RAW_B), -from_raw(RAW_B)))
+    out.append(fadd(from_raw(chunk[4] + carry + RAW_B), -from_raw(RAW_B)))
+    return out
+
+
+def to_u32_plus_2p_gpu(a):
+    two_p = [2 * int(x) for x in PL]
+    carry, chunk = 0, []
+    for i in range(5):
+        v = s64(raw(fadd(a[i], from_raw(RAW_B))) - RAW_B)
+        assert v == int(a[i])
+        t = v + two_p[i] + carry
+        if i < 4: chunk.append(t & ((1 << 52) - 1)); carry = t >> 52
+        else:
+            assert 0 <= t < 1 << 48
+            chunk.append(t)
+    w = [(chunk[0] | (chunk[1] << 52)) & MASK64, ((chunk[1] >> 12) | (chunk[2] << 40)) & MASK64,
+         ((chunk[2] >> 24) | (chunk[3] << 28)) & MASK64, ((chunk[3] >> 36) | (chunk[4] << 16)) & MASK64]
+    words = []
+    for x in w: words += [x & 0xffffffff, x >> 32]
+    return words
+
+
+def _conv_check():
+    rng = random.Random(3)
+    for _ in range(3000):
+        x = rng.choice([0, 1, P - 1, (1 << 256) - 1, rng.randrange(1 << 256), rng.randrange(P)])
+        words = [(x >> (32 * i)) & 0xffffffff for i in range(8)]
+        l = from_u32_gpu(words)
+        assert value(l) == x and all(abs(v) <= HALF for v in l[:4])
+        v = rng.randrange(-2 * P + 1, 2 * P)
+        back = to_u32_plus_2p_gpu(normalize(balanced(v)))
+        assert sum(wd << (32 * i) for i, wd in enumerate(back)) == v + 2 * P
+    print("conversion mirrors ok")
 
 
 def madd_bounds(rounds=30):
@@ -375,4 +449,7 @@ def _check():
 
 if __name__ == '__main__':
     _check()
+    _conv_check()
+    _ec_check()
+    IMPL = _Impl(True)
     _ec_check()
