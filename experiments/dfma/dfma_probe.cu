@@ -10,6 +10,7 @@
 #include "../../circom_compat_b200/csrc/fp.cuh"
 #include "../../circom_compat_b200/csrc/ec.cuh"
 #include "accumulate52.cuh"
+#include "fq2_52.cuh"
 
 using namespace b2g;
 using b2g52::fe52;
@@ -53,6 +54,73 @@ __global__ void ec_check_kernel(fe* __restrict__ out, uint32_t n, uint32_t* __re
     uint32_t w[32];
     b2g52::store52(acc52, w, reduce3);
     for (int c = 0; c < 4; c++) { fe r; for (int j = 0; j < 8; j++) r.l[j] = w[8 * c + j]; out[8 * i + 4 + c] = r; }
+}
+
+using G2c = Curve<Fq2>;
+using b2g52::fe52x2;
+__device__ fe52x2 to52x2(const fe2& x) { fe52x2 r; r.c0 = to52(x.c0); r.c1 = to52(x.c1); return r; }
+__device__ G2c::Aff g2_gen() {       // the standard BN254 G2 generator (same words as csrc/prover.cu: g2_generator)
+    auto w = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+        fe r; r.l[0] = a0; r.l[1] = a1; r.l[2] = a2; r.l[3] = a3; r.l[4] = a4; r.l[5] = a5; r.l[6] = a6; r.l[7] = a7; return Fq::from_canonical(r); };
+    G2c::Aff g;
+    g.x.c0 = w(0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu);
+    g.x.c1 = w(0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u);
+    g.y.c0 = w(0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u);
+    g.y.c1 = w(0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u);
+    return g;
+}
+// G2 counterpart of ec_check_kernel: 6 additions per thread; out[16 i ..] = 8 residues of the integer result, then of the FP64 one
+__global__ void g2_check_kernel(fe* __restrict__ out, uint32_t n, uint32_t* __restrict__ redo_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const G2c::Aff g = g2_gen();
+    G2c::Pt acc = G2c::infinity();
+    b2g52::Pt52x2 acc52; bool first = true, ok = true;
+    for (int k = 0; k < 6; k++) {
+        uint32_t sc[8] = {(i * 6u + k) * 2654435761u + 1u, i ^ (0x9e3779b9u * k), 0, 0, 0, 0, 0, 0};
+        G2c::Aff p = G2c::to_affine(G2c::mul_scalar(G2c::from_affine(g), sc));
+        if (k & 1) p.y = Fq2::neg(p.y);
+        G2c::madd(acc, p);
+        fe52x2 x2 = to52x2(p.x), y2 = to52x2(p.y);
+        if (first) { b2g52::from_affine52_g2(acc52, x2, y2); first = false; }
+        else ok = ok && b2g52::madd52_g2(acc52, x2, y2);
+    }
+    if (!ok) atomicAdd(redo_count, 1u);
+    fe* o = out + 16 * (size_t)i;
+    o[0] = acc.x.c0; o[1] = acc.x.c1; o[2] = acc.y.c0; o[3] = acc.y.c1; o[4] = acc.zz.c0; o[5] = acc.zz.c1; o[6] = acc.zzz.c0; o[7] = acc.zzz.c1;
+    uint32_t w[64];
+    b2g52::store52_g2(acc52, w, reduce3);
+    for (int c = 0; c < 8; c++) { fe r; for (int j = 0; j < 8; j++) r.l[j] = w[8 * c + j]; o[8 + c] = r; }
+}
+// G2 madd throughput, same scheme as madd_probe_kernel (points = pairs of residues from the input buffer)
+__global__ void __launch_bounds__(128) madd_g2_probe_kernel(int mode, int iters, const fe* __restrict__ pts, fe* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool use_fp64 = mode == 1 || (mode == 2 && ((threadIdx.x >> 5) & 1));
+    const fe* my = pts + 4 * (size_t)((i * 37u) & 511u);
+    if (!use_fp64) {
+        G2c::Pt acc = G2c::infinity();
+        #pragma unroll 1
+        for (int k = 0; k < iters; k++) {
+            const fe* q = my + 4 * (k & 31);
+            G2c::Aff p; p.x.c0 = fe_load_nc(q); p.x.c1 = fe_load_nc(q + 1); p.y.c0 = fe_load_nc(q + 2); p.y.c1 = fe_load_nc(q + 3);
+            G2c::madd(acc, p);
+        }
+        out[i] = Fq::add(acc.x.c0, acc.zz.c1);
+    } else {
+        b2g52::Pt52x2 acc;
+        { fe2 x, y; x.c0 = fe_load_nc(my); x.c1 = fe_load_nc(my + 1); y.c0 = fe_load_nc(my + 2); y.c1 = fe_load_nc(my + 3);
+          b2g52::from_affine52_g2(acc, to52x2(x), to52x2(y)); }
+        bool ok = true;
+        #pragma unroll 1
+        for (int k = 1; k < iters; k++) {
+            const fe* q = my + 4 * (k & 31);
+            fe2 x, y; x.c0 = fe_load_nc(q); x.c1 = fe_load_nc(q + 1); y.c0 = fe_load_nc(q + 2); y.c1 = fe_load_nc(q + 3);
+            ok = b2g52::madd52_g2(acc, to52x2(x), to52x2(y)) && ok;
+        }
+        fe r = from52(b2g52::add(acc.X.c0, acc.ZZ.c1));
+        if (!ok) r.l[0] ^= 1u;
+        out[i] = r;
+    }
 }
 
 // compile check of the accumulation kernel (launched by round 2's integration, not by this probe)
@@ -169,6 +237,19 @@ int main(int argc, char** argv) {
         // overkill - take the check kernel's inputs instead: d_in holds residues < p that are not curve points, which is fine
         // for timing (no exceptional case can trigger: the formulas never test curve membership).
     }
+    // 1c. parity of the two G2 mixed additions
+    {
+        const uint32_t ne = 2048;
+        uint32_t* d_redo; CK(cudaMalloc(&d_redo, 4)); CK(cudaMemset(d_redo, 0, 4));
+        g2_check_kernel<<<ne / 64, 64>>>(d_out, ne, d_redo);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> e((size_t)ne * 128); uint32_t redo = 0;
+        CK(cudaMemcpy(e.data(), d_out, (size_t)ne * 512, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&redo, d_redo, 4, cudaMemcpyDeviceToHost));
+        size_t ebad = 0;
+        for (uint32_t i = 0; i < ne; i++) ebad += memcmp(&e[(size_t)i * 128], &e[(size_t)i * 128 + 64], 256) != 0;
+        printf("{\"g2_check\": {\"chains\": %u, \"mismatches\": %zu, \"redo_flags\": %u}}\n", ne, ebad, redo);
+        bad += ebad;
+    }
     // 2. throughput
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int mode = 0; mode < 3; mode++) {
@@ -191,6 +272,17 @@ int main(int argc, char** argv) {
         CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
         float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
         printf("{\"madd_mode\": %d, \"what\": \"%s\", \"ms\": %.3f, \"mixed_adds_per_s\": %.4g}\n", mode,
+               mode == 0 ? "all warps IMAD" : mode == 1 ? "all warps DFMA" : "even warps IMAD, odd warps DFMA", ms, (double)it * n / (ms * 1e-3));
+    }
+    for (int mode = 0; mode < 3; mode++) {
+        const int it = iters / 24 > 32 ? iters / 24 : 32;
+        madd_g2_probe_kernel<<<n / 128, 128>>>(mode, 32, d_in, d_out);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        madd_g2_probe_kernel<<<n / 128, 128>>>(mode, it, d_in, d_out);
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf("{\"madd_g2_mode\": %d, \"what\": \"%s\", \"ms\": %.3f, \"mixed_adds_per_s\": %.4g}\n", mode,
                mode == 0 ? "all warps IMAD" : mode == 1 ? "all warps DFMA" : "even warps IMAD, odd warps DFMA", ms, (double)it * n / (ms * 1e-3));
     }
     return bad ? 2 : 0;

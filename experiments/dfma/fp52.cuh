@@ -59,11 +59,13 @@ __device__ __forceinline__ double column_low(unsigned long long t, unsigned long
     return __dadd_rn(__longlong_as_double(l + B2G52_RAW_B), -B2G52_C52B);
 }
 
-// MODE 0: (a*b + q p) / 2^260     MODE 1: (a*a + q p) / 2^260 (needs |a.l[i]| <= 2^51)     MODE 2: (a*b - c*d + q p) / 2^260
-// Every limb product fed to a split must lie in [-2^103, 2^103].  Columns start at minus the sum of the raw-pattern
-// offsets they are going to receive (in MODE 2 the two product phases cancel each other's offsets).
-template <int MODE>
-__device__ __forceinline__ fe52 mont_core(const fe52& a, const fe52& b, const fe52& c, const fe52& d) {
+// (sum_k s_k * A_k * B_k + q p) / 2^260 with ONE reduction; N <= 4 terms, s_k = -1 where bit k of NEG is set.
+// SQUARE: every term is a square A_k^2 (B_k ignored): upper triangle with doubled cross terms, needs |A_k.l[i]| <= 2^51.
+// Every limb product fed to a split must lie in [-2^103, 2^103].  Columns start at minus the sum of the raw-pattern offsets
+// they are going to receive.  Mirrored line by line by fp52_model.py: mont_sum_gpu.
+template <int N, unsigned NEG, bool SQUARE>
+__device__ __forceinline__ fe52 mont_sum(const fe52& a0, const fe52& b0, const fe52& a1, const fe52& b1,
+                                         const fe52& a2, const fe52& b2, const fe52& a3, const fe52& b3) {
     unsigned long long T[10];
     #pragma unroll
     for (int k = 0; k < 10; k++) {
@@ -72,26 +74,33 @@ __device__ __forceinline__ fe52 mont_core(const fe52& a, const fe52& b, const fe
         for (int i = 0; i < 5; i++)
             #pragma unroll
             for (int j = 0; j < 5; j++) {
-                const bool in_prod = MODE == 0 || (MODE == 1 && j >= i);      // the square touches only the upper triangle
-                if (in_prod && i + j == k) nlo++;
-                if (in_prod && i + j + 1 == k) nhi++;
+                const bool in_prod = !SQUARE || j >= i;
+                #pragma unroll
+                for (int t = 0; t < N; t++) {
+                    const int s = ((NEG >> t) & 1u) ? -1 : 1;
+                    if (in_prod && i + j == k) nlo += s;
+                    if (in_prod && i + j + 1 == k) nhi += s;
+                }
                 if (i + j == k) nlo++;                                        // reduction round i, limb j
                 if (i + j + 1 == k) nhi++;
             }
-        T[k] = 0ull - ((unsigned long long)nlo * (unsigned long long)B2G52_RAW_L + (unsigned long long)nhi * (unsigned long long)B2G52_RAW_H);
+        T[k] = 0ull - ((unsigned long long)(long long)nlo * (unsigned long long)B2G52_RAW_L + (unsigned long long)(long long)nhi * (unsigned long long)B2G52_RAW_H);
     }
     #pragma unroll
-    for (int i = 0; i < 5; i++) {
-        if (MODE == 1) {
-            split_acc<1>(a.l[i], a.l[i], T[2 * i], T[2 * i + 1]);
-            const double a2 = __dadd_rn(a.l[i], a.l[i]);
-            #pragma unroll
-            for (int j = i + 1; j < 5; j++) split_acc<1>(a2, a.l[j], T[i + j], T[i + j + 1]);
-        } else {
-            #pragma unroll
-            for (int j = 0; j < 5; j++) {
-                split_acc<1>(a.l[i], b.l[j], T[i + j], T[i + j + 1]);
-                if (MODE == 2) split_acc<-1>(c.l[i], d.l[j], T[i + j], T[i + j + 1]);
+    for (int t = 0; t < N; t++) {
+        const fe52& a = t == 0 ? a0 : t == 1 ? a1 : t == 2 ? a2 : a3;
+        const fe52& b = t == 0 ? b0 : t == 1 ? b1 : t == 2 ? b2 : b3;
+        const bool neg = (NEG >> t) & 1u;
+        #pragma unroll
+        for (int i = 0; i < 5; i++) {
+            if (SQUARE) {
+                if (neg) split_acc<-1>(a.l[i], a.l[i], T[2 * i], T[2 * i + 1]); else split_acc<1>(a.l[i], a.l[i], T[2 * i], T[2 * i + 1]);
+                const double d2 = __dadd_rn(a.l[i], a.l[i]);
+                #pragma unroll
+                for (int j = i + 1; j < 5; j++) { if (neg) split_acc<-1>(d2, a.l[j], T[i + j], T[i + j + 1]); else split_acc<1>(d2, a.l[j], T[i + j], T[i + j + 1]); }
+            } else {
+                #pragma unroll
+                for (int j = 0; j < 5; j++) { if (neg) split_acc<-1>(a.l[i], b.l[j], T[i + j], T[i + j + 1]); else split_acc<1>(a.l[i], b.l[j], T[i + j], T[i + j + 1]); }
             }
         }
     }
@@ -111,9 +120,9 @@ __device__ __forceinline__ fe52 mont_core(const fe52& a, const fe52& b, const fe
     r.l[4] = __dadd_rn(__longlong_as_double((long long)T[9] + B2G52_RAW_B), -B2G52_C52B);
     return r;
 }
-__device__ __forceinline__ fe52 mont_mul(const fe52& a, const fe52& b) { return mont_core<0>(a, b, a, b); }
-__device__ __forceinline__ fe52 mont_sqr(const fe52& a) { return mont_core<1>(a, a, a, a); }
-__device__ __forceinline__ fe52 mont_mul_sub(const fe52& a, const fe52& b, const fe52& c, const fe52& d) { return mont_core<2>(a, b, c, d); }
+__device__ __forceinline__ fe52 mont_mul(const fe52& a, const fe52& b) { return mont_sum<1, 0u, false>(a, b, a, b, a, b, a, b); }
+__device__ __forceinline__ fe52 mont_sqr(const fe52& a) { return mont_sum<1, 0u, true>(a, a, a, a, a, a, a, a); }            // |a.l[i]| <= 2^51
+__device__ __forceinline__ fe52 mont_mul_sub(const fe52& a, const fe52& b, const fe52& c, const fe52& d) { return mont_sum<2, 2u, false>(a, b, c, d, a, b, a, b); }
 
 __device__ __forceinline__ fe52 add(const fe52& a, const fe52& b) {
     fe52 r;

@@ -397,6 +397,144 @@ def _conv_check():
     print("conversion mirrors ok")
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Fq2 = Fq[u] / (u^2 + 1) and the G2 mixed addition (mirrors fq2_52.cuh).  Every Fq2 product is a pair of signed sums of
+# limb products with ONE reduction each: c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0 (2 x 75 splits); the square is
+# c0 = a0^2 - a1^2 (two triangles, 55 splits), c1 = (2 a0) a1 (50 splits); a*b - c*d is 2 x 125 splits.
+def mont_sum_gpu(terms):
+    """mirror of mont_sum<...>: terms = [(sign, a, b)] with b is None meaning the square of a (upper triangle, doubled cross terms).
+    Returns (sum sign * a * b + q p) / 2^260 with one reduction."""
+    T = []
+    for k in range(10):
+        nlo = nhi = 0
+        for i in range(5):
+            for j in range(5):
+                for sign, a, b in terms:
+                    in_prod = (b is not None) or j >= i
+                    nlo += sign * (in_prod and i + j == k); nhi += sign * (in_prod and i + j + 1 == k)
+                nlo += (i + j == k); nhi += (i + j + 1 == k)
+        T.append((-(nlo * RAW_L + nhi * RAW_H)) & MASK64)
+    for sign, a, b in terms:
+        f = split_acc if sign > 0 else split_sub
+        for i in range(5):
+            if b is None:
+                f(a[i], a[i], T, 2 * i, 2 * i + 1)
+                a2 = fadd(a[i], a[i])
+                for j in range(i + 1, 5): f(a2, a[j], T, i + j, i + j + 1)
+            else:
+                for j in range(5): f(a[i], b[j], T, i + j, i + j + 1)
+    for i in range(5):
+        l, _ = column_low(T[i] + RAW_L)
+        q = split_low(l, PINV_B)
+        for j in range(5): split_acc(q, PL[j], T, i + j, i + j + 1)
+        assert s64(T[i]) % (1 << 52) == 0
+        T[i + 1] = (T[i + 1] + (s64(T[i]) >> 52)) & MASK64
+    r = []
+    for k in range(5, 9):
+        l, c_ = column_low(T[k]); T[k + 1] = (T[k + 1] + c_) & MASK64; r.append(l)
+    t9 = s64(T[9]); assert abs(t9) < 1 << 51
+    r.append(fadd(from_raw(t9 + RAW_B), -from_raw(RAW_B)))
+    return r
+
+
+def mul2(a, b):       return (mont_sum_gpu([(1, a[0], b[0]), (-1, a[1], b[1])]), mont_sum_gpu([(1, a[0], b[1]), (1, a[1], b[0])]))
+def sqr2(a):          return (mont_sum_gpu([(1, a[0], None), (-1, a[1], None)]), mont_sum_gpu([(1, ladd(a[0], a[0]), a[1])]))
+def mul_sub2(a, b, c, d):
+    return (mont_sum_gpu([(1, a[0], b[0]), (-1, a[1], b[1]), (-1, c[0], d[0]), (1, c[1], d[1])]),
+            mont_sum_gpu([(1, a[0], b[1]), (1, a[1], b[0]), (-1, c[0], d[1]), (-1, c[1], d[0])]))
+def add2(a, b):       return (ladd(a[0], b[0]), ladd(a[1], b[1]))
+def sub2(a, b):       return (lsub(a[0], b[0]), lsub(a[1], b[1]))
+def norm2(a):         return (normalize(a[0]), normalize(a[1]))
+def val2(a):          return (value(a[0]), value(a[1]))
+
+
+def madd52_g2(acc, xt, yt, negate=False):
+    """G2 counterpart of madd52; xt, yt = (c0, c1) residue pairs in the 2^256 domain"""
+    if xt == (0, 0) and yt == (0, 0): return
+    x2 = (balanced(xt[0]), balanced(xt[1])); y2 = (balanced(yt[0]), balanced(yt[1]))
+    if negate: y2 = ([-v for v in y2[0]], [-v for v in y2[1]])
+    if acc.inf:
+        k = (list(K264), [0.0] * 5)
+        acc.X, acc.Y = mul2(x2, k), mul2(y2, k)
+        acc.ZZ, acc.ZZZ = k, k
+        acc.inf = False
+        return
+    U2, S2 = mul2(x2, acc.ZZ), mul2(y2, acc.ZZZ)
+    Pn, Rn = norm2(sub2(U2, acc.X)), norm2(sub2(S2, acc.Y))
+    if abs(Pn[0][0]) in CAND and abs(Pn[1][0]) in CAND:
+        acc.redo = True
+        return
+    PP = sqr2(Pn); PPP = mul2(Pn, PP); Q = mul2(acc.X, PP); RR = sqr2(Rn)
+    X3 = norm2(sub2(sub2(RR, PPP), add2(Q, Q)))
+    Y3 = mul_sub2(Rn, sub2(Q, X3), acc.Y, PPP)
+    acc.ZZ, acc.ZZZ = mul2(acc.ZZ, PP), mul2(acc.ZZZ, PPP)
+    acc.X, acc.Y = X3, Y3
+    for v in (acc.X, acc.Y, acc.ZZ, acc.ZZZ):
+        assert max(abs(value(v[0])), abs(value(v[1]))) < 3 * P
+
+
+def _g2_check():
+    rng = random.Random(11)
+    R256 = pow(2, 256, P); R256i = pow(R256, -1, P); rinv = pow(R, -1, P)
+    # Fq2 helpers on integers
+    f2mul = lambda a, b: ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+    f2sub = lambda a, b: ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+    def f2inv(a):
+        d = pow(a[0] * a[0] + a[1] * a[1], -1, P); return (a[0] * d % P, -a[1] * d % P)
+    # field-level checks against integers
+    for _ in range(300):
+        a = (balanced(rng.randrange(-2 * P, 2 * P)), balanced(rng.randrange(-2 * P, 2 * P)))
+        b = (balanced(rng.randrange(-2 * P, 2 * P)), balanced(rng.randrange(-2 * P, 2 * P)))
+        c = (balanced(rng.randrange(-P, P)), balanced(rng.randrange(-P, P)))
+        d = (balanced(rng.randrange(-P, P)), balanced(rng.randrange(-P, P)))
+        m = val2(mul2(a, b)); e = f2mul(val2(a), val2(b))
+        assert (m[0] - e[0] * rinv) % P == 0 and (m[1] - e[1] * rinv) % P == 0
+        q = val2(sqr2(a)); e = f2mul(val2(a), val2(a))
+        assert (q[0] - e[0] * rinv) % P == 0 and (q[1] - e[1] * rinv) % P == 0
+        ms = val2(mul_sub2(a, b, c, d)); e = f2sub(f2mul(val2(a), val2(b)), f2mul(val2(c), val2(d)))
+        assert (ms[0] - e[0] * rinv) % P == 0 and (ms[1] - e[1] * rinv) % P == 0
+    # curve-level: the twist y^2 = x^3 + 3 / (9 + u); points by cofactor-free trial (any point of E'(Fq2) works for the formulas)
+    bt = f2mul((3, 0), f2inv((9, 1)))
+    def f2sqrt(a):
+        # Fq2 square root by the complex method (p = 3 mod 4)
+        if a == (0, 0): return (0, 0)
+        n = (a[0] * a[0] + a[1] * a[1]) % P
+        s = pow(n, (P + 1) // 4, P)
+        if s * s % P != n: return None
+        for sgn in (1, -1):
+            t = (a[0] + sgn * s) * pow(2, -1, P) % P
+            x0 = pow(t, (P + 1) // 4, P)
+            if x0 * x0 % P == t and x0:
+                x1 = a[1] * pow(2 * x0, -1, P) % P
+                if f2mul((x0, x1), (x0, x1)) == a: return (x0, x1)
+        return None
+    def rand_point():
+        while True:
+            x = (rng.randrange(P), rng.randrange(P))
+            rhs = tuple((u + v) % P for u, v in zip(f2mul(f2mul(x, x), x), bt))
+            y = f2sqrt(rhs)
+            if y is not None: return x, y
+    def aff_add(p, q):
+        if p is None: return q
+        (x1, y1), (x2, y2) = p, q
+        assert x1 != x2
+        lam = f2mul(f2sub(y2, y1), f2inv(f2sub(x2, x1)))
+        x3 = f2sub(f2sub(f2mul(lam, lam), x1), x2)
+        return x3, f2sub(f2mul(lam, f2sub(x1, x3)), y1)
+    for trial in range(6):
+        acc, ref = Acc52(), None
+        for k in range(10):
+            x, y = rand_point(); neg = rng.random() < 0.5
+            madd52_g2(acc, tuple(v * R256 % P for v in x), tuple(v * R256 % P for v in y), neg)
+            ref = aff_add(ref, (x, tuple((P - v) % P for v in y) if neg else y))
+        assert not acc.redo
+        k256 = (list(K256), [0.0] * 5); k252 = (list(K252), [0.0] * 5)
+        X = tuple(v * R256i % P for v in val2(mul2(acc.X, k256))); Y = tuple(v * R256i % P for v in val2(mul2(acc.Y, k256)))
+        ZZ = tuple(v * R256i % P for v in val2(mul2(acc.ZZ, k252))); ZZZ = tuple(v * R256i % P for v in val2(mul2(acc.ZZZ, k252)))
+        assert (f2mul(X, f2inv(ZZ)), f2mul(Y, f2inv(ZZZ))) == ref
+    print("fq2 / g2 model ok")
+
+
 def madd_bounds(rounds=30):
     """fixed point of the XYZZ mixed-addition magnitudes (in units of p) under almost-Montgomery products"""
     f = lambda a, b: 0.0118 * a * b + 0.5
@@ -453,3 +591,4 @@ if __name__ == '__main__':
     _ec_check()
     IMPL = _Impl(True)
     _ec_check()
+    _g2_check()
