@@ -207,15 +207,27 @@ __global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kerne
 #include "../../experiments/dfma/accumulate52.cuh"
 namespace b2g {
 // (4b) experiments/dfma, UNMEASURED, compiled only with -DB2G_ENABLE_FP64_ACC: threads [t_begin, t_end) of the same run
-// list on the FP64 pipe (DFMA + integer adds instead of IMAD.WIDE); see experiments/dfma/README.md
+// list on the FP64 pipe (DFMA + integer adds instead of IMAD.WIDE); see experiments/dfma/README.md.
+// PERSISTENT: a small grid (a fixed number of CTAs per SM) pulls 128-run blocks from a counter, so that its CTAs stay
+// resident next to the integer kernel's for the whole accumulation - two large ordinary grids would simply run one after
+// the other, and the two multiplier pipes would never be busy together.
 __global__ void __launch_bounds__(128, 4) msm_accumulate52_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
                                       const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk, void* __restrict__ buckets,
                                       void* __restrict__ frag_first, void* __restrict__ frag_last, uint32_t t_begin, uint32_t t_end,
-                                      uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count) {
-    const uint32_t t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= t_end) return;
-    b2g52::accumulate52_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
-                            [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
+                                      uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count, uint32_t* __restrict__ work_counter) {
+    __shared__ uint32_t blk_sh;
+    const uint32_t nblk = (t_end - t_begin + 127u) / 128u;
+    for (;;) {
+        if (threadIdx.x == 0) blk_sh = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t blk = blk_sh;
+        __syncthreads();
+        if (blk >= nblk) return;
+        const uint32_t t = t_begin + blk * 128u + threadIdx.x;
+        if (t < t_end)
+            b2g52::accumulate52_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
+                                    [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
+    }
 }
 // runs handed back by the FP64 kernel, replayed with the complete addition law (same body as msm_accumulate_kernel)
 template <class C, class F>
@@ -429,8 +441,9 @@ void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, b
     if (s.fp64_share > 100) s.fp64_share = 100;
     if (s.fp64_share) {
         CUDA_CHECK(cudaMalloc(&s.redo_list, nchunks * 4));
-        CUDA_CHECK(cudaMalloc(&s.redo_count, 4));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&s.fp64, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaMalloc(&s.redo_count, 8));           // [0] replay count, [1] work counter of the persistent FP64 grid
+        { int least = 0, greatest = 0; CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+          CUDA_CHECK(cudaStreamCreateWithPriority(&s.fp64, cudaStreamNonBlocking, greatest)); }   // its few persistent CTAs are placed first
         CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     }
@@ -491,11 +504,14 @@ static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmS
     if (!plan.g2 && s.fp64) {
         // runs [n_int, nthreads) go to the FP64-pipe kernel on its own stream; both kernels are resident together
         n_int = (uint32_t)((uint64_t)nthreads * (100 - s.fp64_share) / 100) & ~127u;
-        CUDA_CHECK(cudaMemsetAsync(s.redo_count, 0, 4, st));
+        CUDA_CHECK(cudaMemsetAsync(s.redo_count, 0, 8, st));
         CUDA_CHECK(cudaEventRecord(s.ev_fork, st));
         CUDA_CHECK(cudaStreamWaitEvent(s.fp64, s.ev_fork, 0));
-        msm_accumulate52_kernel<<<(nthreads - n_int + 127) / 128, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
-                                                                                   n_int, nthreads, s.redo_list, s.redo_count);
+        static int sm_count = 0;
+        if (!sm_count) { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)); }
+        const uint32_t want = (uint32_t)sm_count * env_u32("B2G_MSM_FP64_CTAS", 2), have = (nthreads - n_int + 127) / 128;
+        msm_accumulate52_kernel<<<want < have ? want : have, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
+                                                                               n_int, nthreads, s.redo_list, s.redo_count, s.redo_count + 1);
         CUDA_CHECK(cudaEventRecord(s.ev_join, s.fp64));
         if (n_int) msm_accumulate_kernel<C, F><<<n_int / 128, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
         CUDA_CHECK(cudaStreamWaitEvent(st, s.ev_join, 0));
