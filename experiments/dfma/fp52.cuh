@@ -54,7 +54,7 @@ __device__ __forceinline__ double split_low(double a, double b) {
 // signed 64-bit column value -> balanced low limb (as a double, |l| <= 2^51); the carry is added to `next`
 __device__ __forceinline__ double column_low(unsigned long long t, unsigned long long& next) {
     const long long c = ((long long)t + (1ll << 51)) >> 52;
-    const long long l = (long long)t - (c << 52);
+    const long long l = (long long)(t - ((unsigned long long)c << 52));
     next += (unsigned long long)c;
     return __dadd_rn(__longlong_as_double(l + B2G52_RAW_B), -B2G52_C52B);
 }
@@ -178,7 +178,7 @@ __device__ __forceinline__ fe52 from_u32(const uint32_t* x) {
     for (int i = 0; i < 4; i++) {
         long long t = chunk[i] + carry;
         carry = (t + (1ll << 51)) >> 52;                     // 0 or 1
-        t -= carry << 52;
+        t -= (long long)((unsigned long long)carry << 52);
         r.l[i] = __dadd_rn(__longlong_as_double(t + B2G52_RAW_B), -B2G52_C52B);
     }
     r.l[4] = __dadd_rn(__longlong_as_double(chunk[4] + carry + B2G52_RAW_B), -B2G52_C52B);
