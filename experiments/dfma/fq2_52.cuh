@@ -10,24 +10,27 @@ namespace b2g52 {
 
 struct fe52x2 { fe52 c0, c1; };
 
-__device__ __forceinline__ fe52x2 mul2(const fe52x2& a, const fe52x2& b) {
-    fe52x2 r;
-    r.c0 = mont_sum<2, 2u, false>(a.c0, b.c0, a.c1, b.c1, a.c0, b.c0, a.c0, b.c0);
-    r.c1 = mont_sum<2, 0u, false>(a.c0, b.c1, a.c1, b.c0, a.c0, b.c0, a.c0, b.c0);
-    return r;
+// The six wide sums below are ~350 - 840 instructions each; fully inlined a G2 mixed addition is 9 000 instructions (144 KB,
+// past the instruction cache).  -DB2G52_FQ2_CALL=__noinline__ turns them into real calls (operands by reference in local
+// memory, 54 KB of code in total); which one wins is a measurement for round 2.
+#ifndef B2G52_FQ2_CALL
+#define B2G52_FQ2_CALL __forceinline__
+#endif
+__device__ B2G52_FQ2_CALL fe52 fq2_mul_c0(const fe52x2& a, const fe52x2& b) { return mont_sum<2, 2u, false>(a.c0, b.c0, a.c1, b.c1, a.c0, b.c0, a.c0, b.c0); }
+__device__ B2G52_FQ2_CALL fe52 fq2_mul_c1(const fe52x2& a, const fe52x2& b) { return mont_sum<2, 0u, false>(a.c0, b.c1, a.c1, b.c0, a.c0, b.c0, a.c0, b.c0); }
+__device__ B2G52_FQ2_CALL fe52 fq2_sqr_c0(const fe52x2& a) { return mont_sum<2, 2u, true>(a.c0, a.c0, a.c1, a.c1, a.c0, a.c0, a.c0, a.c0); }
+__device__ B2G52_FQ2_CALL fe52 fq2_sqr_c1(const fe52x2& a) { return mont_mul(add(a.c0, a.c0), a.c1); }
+__device__ B2G52_FQ2_CALL fe52 fq2_mul_sub_c0(const fe52x2& a, const fe52x2& b, const fe52x2& c, const fe52x2& d) {
+    return mont_sum<4, 6u, false>(a.c0, b.c0, a.c1, b.c1, c.c0, d.c0, c.c1, d.c1);      // + - - +
 }
+__device__ B2G52_FQ2_CALL fe52 fq2_mul_sub_c1(const fe52x2& a, const fe52x2& b, const fe52x2& c, const fe52x2& d) {
+    return mont_sum<4, 12u, false>(a.c0, b.c1, a.c1, b.c0, c.c0, d.c1, c.c1, d.c0);     // + + - -
+}
+__device__ __forceinline__ fe52x2 mul2(const fe52x2& a, const fe52x2& b) { fe52x2 r; r.c0 = fq2_mul_c0(a, b); r.c1 = fq2_mul_c1(a, b); return r; }
 // both components of a must be limb-normalised (|l| <= 2^51)
-__device__ __forceinline__ fe52x2 sqr2(const fe52x2& a) {
-    fe52x2 r;
-    r.c0 = mont_sum<2, 2u, true>(a.c0, a.c0, a.c1, a.c1, a.c0, a.c0, a.c0, a.c0);
-    r.c1 = mont_mul(add(a.c0, a.c0), a.c1);
-    return r;
-}
+__device__ __forceinline__ fe52x2 sqr2(const fe52x2& a) { fe52x2 r; r.c0 = fq2_sqr_c0(a); r.c1 = fq2_sqr_c1(a); return r; }
 __device__ __forceinline__ fe52x2 mul_sub2(const fe52x2& a, const fe52x2& b, const fe52x2& c, const fe52x2& d) {
-    fe52x2 r;
-    r.c0 = mont_sum<4, 6u, false>(a.c0, b.c0, a.c1, b.c1, c.c0, d.c0, c.c1, d.c1);      // + - - +
-    r.c1 = mont_sum<4, 12u, false>(a.c0, b.c1, a.c1, b.c0, c.c0, d.c1, c.c1, d.c0);     // + + - -
-    return r;
+    fe52x2 r; r.c0 = fq2_mul_sub_c0(a, b, c, d); r.c1 = fq2_mul_sub_c1(a, b, c, d); return r;
 }
 __device__ __forceinline__ fe52x2 add2(const fe52x2& a, const fe52x2& b) { fe52x2 r; r.c0 = add(a.c0, b.c0); r.c1 = add(a.c1, b.c1); return r; }
 __device__ __forceinline__ fe52x2 sub2(const fe52x2& a, const fe52x2& b) { fe52x2 r; r.c0 = sub(a.c0, b.c0); r.c1 = sub(a.c1, b.c1); return r; }
