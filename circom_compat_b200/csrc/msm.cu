@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kerne
 
 #ifdef B2G_ENABLE_FP64_ACC
 }  // namespace b2g
+#ifndef B2G52_FQ2_CALL
+#define B2G52_FQ2_CALL __noinline__
+#endif
 #include "../../experiments/dfma/accumulate52.cuh"
 namespace b2g {
 // (4b) experiments/dfma, UNMEASURED, compiled only with -DB2G_ENABLE_FP64_ACC: threads [t_begin, t_end) of the same run
@@ -227,6 +230,25 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate52_kernel(const void* __
         if (t < t_end)
             b2g52::accumulate52_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
                                     [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
+    }
+}
+// G2 counterpart (3 CTAs per SM like the integer G2 kernel; the Fq2 wide sums are calls: -DB2G52_FQ2_CALL=__noinline__)
+__global__ void __launch_bounds__(128, 2) msm_accumulate52_g2_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
+                                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk, void* __restrict__ buckets,
+                                      void* __restrict__ frag_first, void* __restrict__ frag_last, uint32_t t_begin, uint32_t t_end,
+                                      uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count, uint32_t* __restrict__ work_counter) {
+    __shared__ uint32_t blk_sh;
+    const uint32_t nblk = (t_end - t_begin + 127u) / 128u;
+    for (;;) {
+        if (threadIdx.x == 0) blk_sh = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t blk = blk_sh;
+        __syncthreads();
+        if (blk >= nblk) return;
+        const uint32_t t = t_begin + blk * 128u + threadIdx.x;
+        if (t < t_end)
+            b2g52::accumulate52_g2_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
+                                       [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
     }
 }
 // runs handed back by the FP64 kernel, replayed with the complete addition law (same body as msm_accumulate_kernel)
@@ -437,7 +459,7 @@ void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, b
     CUDA_CHECK(cudaMalloc(&s.partials, (npart + 1) * pt));
     CUDA_CHECK(cudaMalloc(&s.result, pt)); s.result_owned = true;
 #ifdef B2G_ENABLE_FP64_ACC
-    s.fp64_share = g2 ? 0 : env_u32("B2G_MSM_FP64_SHARE", 0);
+    s.fp64_share = env_u32(g2 ? "B2G_MSM_FP64_SHARE_G2" : "B2G_MSM_FP64_SHARE", 0);
     if (s.fp64_share > 100) s.fp64_share = 100;
     if (s.fp64_share) {
         CUDA_CHECK(cudaMalloc(&s.redo_list, nchunks * 4));
@@ -501,7 +523,7 @@ static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmS
     if (s.prof0) CUDA_CHECK(cudaEventRecord(s.prof0, st));
 #ifdef B2G_ENABLE_FP64_ACC
     uint32_t n_int = nthreads;
-    if (!plan.g2 && s.fp64) {
+    if (s.fp64) {
         // runs [n_int, nthreads) go to the FP64-pipe kernel on its own stream; both kernels are resident together
         n_int = (uint32_t)((uint64_t)nthreads * (100 - s.fp64_share) / 100) & ~127u;
         CUDA_CHECK(cudaMemsetAsync(s.redo_count, 0, 8, st));
@@ -509,9 +531,13 @@ static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmS
         CUDA_CHECK(cudaStreamWaitEvent(s.fp64, s.ev_fork, 0));
         static int sm_count = 0;
         if (!sm_count) { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)); }
-        const uint32_t want = (uint32_t)sm_count * env_u32("B2G_MSM_FP64_CTAS", 2), have = (nthreads - n_int + 127) / 128;
-        msm_accumulate52_kernel<<<want < have ? want : have, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
-                                                                               n_int, nthreads, s.redo_list, s.redo_count, s.redo_count + 1);
+        const uint32_t want = (uint32_t)sm_count * env_u32(plan.g2 ? "B2G_MSM_FP64_CTAS_G2" : "B2G_MSM_FP64_CTAS", plan.g2 ? 1 : 2), have = (nthreads - n_int + 127) / 128;
+        if (plan.g2)
+            msm_accumulate52_g2_kernel<<<want < have ? want : have, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
+                                                                                      n_int, nthreads, s.redo_list, s.redo_count, s.redo_count + 1);
+        else
+            msm_accumulate52_kernel<<<want < have ? want : have, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
+                                                                                   n_int, nthreads, s.redo_list, s.redo_count, s.redo_count + 1);
         CUDA_CHECK(cudaEventRecord(s.ev_join, s.fp64));
         if (n_int) msm_accumulate_kernel<C, F><<<n_int / 128, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
         CUDA_CHECK(cudaStreamWaitEvent(st, s.ev_join, 0));

@@ -9,6 +9,7 @@
 // replays those runs with the integer kernel afterwards (it overwrites whatever this kernel had stored for them).
 #pragma once
 #include "ec52.cuh"
+#include "fq2_52.cuh"
 
 namespace b2g52 {
 
@@ -62,6 +63,67 @@ __device__ __forceinline__ void accumulate52_run(uint32_t t, const void* __restr
                        : (seg_start == start)                         ? reinterpret_cast<uint4*>(static_cast<uint8_t*>(frag_first) + (size_t)t * 128)
                                                                       : reinterpret_cast<uint4*>(static_cast<uint8_t*>(frag_last) + (size_t)t * 128);
             store_point52(acc, inf, dst, reduce_once);
+            inf = true;
+            seg_start = pos;
+            if (pos == bucket_end && pos < end) {
+                do { b++; bucket_end = offsets[b + 1]; } while (bucket_end <= pos);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- G2
+template <class ReduceOnce>
+__device__ __forceinline__ void store_point52_g2(const Pt52x2& acc, bool inf, uint4* dst, ReduceOnce reduce_once) {
+    uint32_t w[64];
+    if (inf) {
+        #pragma unroll
+        for (int i = 0; i < 64; i++) w[i] = 0;
+    } else {
+        store52_g2(acc, w, [&](uint32_t* v) { reduce_once(v); reduce_once(v); reduce_once(v); });
+    }
+    #pragma unroll
+    for (int i = 0; i < 16; i++) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
+// G2 counterpart of accumulate52_run: table rows are 128 B (x.c0, x.c1, y.c0, y.c1), points 256 B
+template <class ReduceOnce>
+__device__ __forceinline__ void accumulate52_g2_run(uint32_t t, const void* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                    const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
+                                                    void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last,
+                                                    uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count, ReduceOnce reduce_once) {
+    const uint32_t total = offsets[nb];
+    const uint64_t start64 = (uint64_t)t * chunk;
+    if (start64 >= total) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (uint32_t)min((uint64_t)total, start64 + chunk);
+    uint32_t lo = 0, hi = nb;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= start) lo = mid; else hi = mid; }
+    uint32_t b = lo;
+    uint32_t bucket_end = offsets[b + 1];
+    while (bucket_end <= start) { b++; bucket_end = offsets[b + 1]; }
+    Pt52x2 acc; bool inf = true;
+    uint32_t seg_start = start;
+    for (uint32_t pos = start; pos < end;) {
+        const uint32_t e = entries[pos];
+        const uint4* row = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(table) + (size_t)(e & 0x7fffffffu) * 128);
+        uint32_t w[32]; uint32_t any = 0;
+        #pragma unroll
+        for (int i = 0; i < 8; i++) { const uint4 r = __ldg(row + i); w[4 * i] = r.x; w[4 * i + 1] = r.y; w[4 * i + 2] = r.z; w[4 * i + 3] = r.w; any |= r.x | r.y | r.z | r.w; }
+        if (any) {
+            fe52x2 x2, y2;
+            x2.c0 = from_u32(w); x2.c1 = from_u32(w + 8); y2.c0 = from_u32(w + 16); y2.c1 = from_u32(w + 24);
+            if (e >> 31) y2 = neg2(y2);
+            if (inf) { from_affine52_g2(acc, x2, y2); inf = false; }
+            else if (!madd52_g2(acc, x2, y2)) { redo_list[atomicAdd(redo_count, 1u)] = t; return; }
+        }
+        pos++;
+        if (pos == bucket_end || pos == end) {
+            const uint32_t bucket_start = offsets[b];
+            uint4* dst = (bucket_start >= start && bucket_end <= end) ? reinterpret_cast<uint4*>(static_cast<uint8_t*>(buckets) + (size_t)b * 256)
+                       : (seg_start == start)                         ? reinterpret_cast<uint4*>(static_cast<uint8_t*>(frag_first) + (size_t)t * 256)
+                                                                      : reinterpret_cast<uint4*>(static_cast<uint8_t*>(frag_last) + (size_t)t * 256);
+            store_point52_g2(acc, inf, dst, reduce_once);
             inf = true;
             seg_start = pos;
             if (pos == bucket_end && pos < end) {

@@ -10,7 +10,6 @@
 #include "../../circom_compat_b200/csrc/fp.cuh"
 #include "../../circom_compat_b200/csrc/ec.cuh"
 #include "accumulate52.cuh"
-#include "fq2_52.cuh"
 
 using namespace b2g;
 using b2g52::fe52;
