@@ -197,6 +197,52 @@ __global__ void __launch_bounds__(128) probe_kernel(int mode, int iters, const f
     }
 }
 
+
+// ---- pipe micro-benchmarks: 8 independent chains per thread of one instruction kind, to read off issue rates
+//   kind 0 DFMA (rn)   1 DFMA.RM (round down)   2 DADD   3 IMAD.WIDE.U32   4 64-bit integer add (IADD3 + IADD3.X)
+//   kind 5: even warps IMAD.WIDE, odd warps DFMA (rn)     kind 6: even warps IMAD.WIDE, odd warps 64-bit adds
+__global__ void __launch_bounds__(256) pipe_probe_kernel(int kind, int iters, double seed, double* __restrict__ out, unsigned long long* __restrict__ clk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int odd = (threadIdx.x >> 5) & 1;
+    int k = kind;
+    if (kind == 5) k = odd ? 0 : 3;
+    if (kind == 6) k = odd ? 4 : 3;
+    double d[8]; unsigned long long u[8]; uint32_t m = (uint32_t)seed | 1u;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) { d[j] = seed + j + i * 1e-9; u[j] = (unsigned long long)(i + j) * 0x9e3779b97f4a7c15ull; }
+    const double a = 1.0000001, b = seed * 1e-7;
+    unsigned long long t0 = 0, g0 = 0;
+    if (i == 0) { t0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0)); }
+    #pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+        if (k == 0) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = __fma_rn(d[j], a, b);
+        } else if (k == 1) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = __fma_rd(d[j], a, b);
+        } else if (k == 2) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = __dadd_rn(d[j], b);
+        } else if (k == 3) {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(u[j]) : "r"((uint32_t)u[j]), "r"(m));
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t lo = (uint32_t)u[j], hi = (uint32_t)(u[j] >> 32);
+                asm volatile("add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, %3;" : "+r"(lo), "+r"(hi) : "r"(m), "r"((uint32_t)it));
+                u[j] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+            }
+        }
+    }
+    if (i == 0) { unsigned long long t1 = clock64(), g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1)); clk[0] = t1 - t0; clk[1] = g1 - g0; }
+    double r = 0; unsigned long long q = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) { r += d[j]; q ^= u[j]; }
+    out[i] = r + (double)q;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
 int main(int argc, char** argv) {
@@ -248,6 +294,27 @@ int main(int argc, char** argv) {
         for (uint32_t i = 0; i < ne; i++) ebad += memcmp(&e[(size_t)i * 128], &e[(size_t)i * 128 + 64], 256) != 0;
         printf("{\"g2_check\": {\"chains\": %u, \"mismatches\": %zu, \"redo_flags\": %u}}\n", ne, ebad, redo);
         bad += ebad;
+    }
+    // 0. pipe micro-benchmarks (and the SM clock under each load: clock64 / globaltimer of one thread)
+    {
+        double* d_o; unsigned long long* d_clk; CK(cudaMalloc(&d_o, (size_t)n * 8)); CK(cudaMalloc(&d_clk, 16));
+        cudaEvent_t a0, a1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1));
+        const char* names[7] = {"DFMA rn", "DFMA rd (.RM)", "DADD", "IMAD.WIDE.U32", "64-bit add", "even IMAD.WIDE / odd DFMA", "even IMAD.WIDE / odd 64-bit add"};
+        int dev = 0, sms = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const uint32_t np = (uint32_t)sms * 2048u;                        // full occupancy: 8 CTAs of 256 threads per SM
+        for (int kind = 0; kind < 7; kind++) {
+            const int it = 4096;
+            pipe_probe_kernel<<<np / 256, 256>>>(kind, 64, 3.0, d_o, d_clk);
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventRecord(a0));
+            pipe_probe_kernel<<<np / 256, 256>>>(kind, it, 3.0, d_o, d_clk);
+            CK(cudaEventRecord(a1)); CK(cudaDeviceSynchronize());
+            float ms = 0; CK(cudaEventElapsedTime(&ms, a0, a1));
+            unsigned long long c[2]; CK(cudaMemcpy(c, d_clk, 16, cudaMemcpyDeviceToHost));
+            const double ops = 8.0 * it * np, mhz = c[1] ? 1e3 * (double)c[0] / (double)c[1] : 0.0;
+            printf("{\"pipe\": \"%s\", \"ms\": %.3f, \"thread_ops_per_s\": %.4g, \"lanes_per_clk_per_sm\": %.1f, \"sm_mhz\": %.0f}\n",
+                   names[kind], ms, ops / (ms * 1e-3), mhz > 0 ? ops / (ms * 1e-3) / (mhz * 1e6) / sms : 0.0, mhz);
+        }
     }
     // 2. throughput
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
