@@ -1,7 +1,7 @@
 // groth16_bench.cpp - C++ counterpart of /root/reference/benches/groth16.rs:13-85: read a zkey, obtain the full assignment,
 // draw / take (r, s), call Groth16::create_proof_with_reduction_and_matrices repeatedly and report the time per proof.
 //
-//   groth16_bench --parse-only <circuit.zkey>                      host-only: print what read_zkey produced (no GPU)
+//   groth16_bench --parse-only <circuit.zkey> [--dump-key]         host-only: print what read_zkey produced (no GPU)
 //   groth16_bench <circuit.zkey> chain:<a>|<witness.wtns> [iters] [r_hex s_hex]
 //       chain:<a> = the witness of the reference's squaring-chain bench family for input a
 //       (test-vectors/complex-circuit/input.json has a = 3), computed on the host instead of by WASM.
@@ -61,6 +61,22 @@ int main(int argc, char** argv) {
             for (const Matrix* mm : {&m.a, &m.b})
                 for (const auto& row : *mm) for (const auto& e : row) { hc = fnv(e.first.l, 32, hc); uint32_t c = (uint32_t)e.second; hc = fnv(&c, 4, hc); }
             std::printf("fnv coefs=%016llx\n", (unsigned long long)hc);
+            if (argc >= 4 && std::string(argv[3]) == "--dump-key") {       // every query point as the zkey's own bytes (small keys)
+                auto dump = [](const char* name, const void* p, size_t count, size_t stride) {
+                    const uint8_t* b = (const uint8_t*)p;
+                    for (size_t i = 0; i < count; i++) {
+                        std::printf("%s[%zu]=", name, i);
+                        for (size_t k = 0; k < stride; k++) std::printf("%02x", b[i * stride + k]);
+                        std::printf("\n");
+                    }
+                };
+                dump("gamma_abc_g1", pk.vk.gamma_abc_g1.data(), pk.vk.gamma_abc_g1.size(), 64);
+                dump("a_query", pk.a_query.data(), pk.a_query.size(), 64);
+                dump("b_g1_query", pk.b_g1_query.data(), pk.b_g1_query.size(), 64);
+                dump("b_g2_query", pk.b_g2_query.data(), pk.b_g2_query.size(), 128);
+                dump("l_query", pk.l_query.data(), pk.l_query.size(), 64);
+                dump("h_query", pk.h_query.data(), pk.h_query.size(), 64);
+            }
             return 0;
         }
         if (argc < 3) { std::fprintf(stderr, "usage: %s [--parse-only] <zkey> chain:<a>|<wtns> [iters] [r_hex s_hex]\n", argv[0]); return 2; }

@@ -227,6 +227,8 @@ def setup_scalars(circ: Circuit, seed: int = 0xB200, trapdoor=None, flavour: str
     h_t = h_query_scalars(n, tau, dinv) if flavour == 'circom' else h_query_scalars_libsnark(n, tau, dinv)
     td = Trapdoor(tau, alpha, beta, delta, a_t, b_t, l_t, h_t, [x * ginv % R_MOD for x in abc[:li]])
     td.gamma = gamma
+    td.lagrange = L                     # L_row(tau), row < n: lets the expected proof be computed without any h (see below)
+    td.flavour = flavour
     return td
 
 
@@ -260,8 +262,46 @@ def generate_random_parameters_with_reduction(circ: Circuit, rng, ctx, flavour: 
     return pk
 
 
+def qap_numerator_at_tau(td: Trapdoor, circ: Circuit, w):
+    """(a*b - c)(tau) computed WITHOUT any transform and without the C matrix: a, b are the interpolants of the row
+    evaluations <A_row, w>, <B_row, w> (plus the public-input rows of A, qap.rs:46-50) and c interpolates their
+    pointwise product (qap.rs:52-58), so a(tau) = sum_row a_row L_row(tau) etc.  O(nnz) big-int work.  This is the
+    quantity sum_j h_j * h_t[j] * delta must equal; it never touches the witness map under test."""
+    m, li, L = circ.num_constraints, circ.num_inputs, td.lagrange
+    ra = [0] * m
+    rb = [0] * m
+    for (rows, cols, vals), tgt in ((circ.A, ra), (circ.B, rb)):
+        for r_, c_, v in zip(np.asarray(rows).tolist(), np.asarray(cols).tolist(), vals):
+            if v:
+                tgt[r_] = (tgt[r_] + v * w[c_]) % R_MOD
+    at = bt = ct = 0
+    for i in range(m):
+        li_ = L[i]
+        at += ra[i] * li_
+        bt += rb[i] * li_
+        ct += (ra[i] * rb[i] % R_MOD) * li_
+    for j in range(li):
+        at += w[j] * L[m + j]
+    return (at % R_MOD) * (bt % R_MOD) % R_MOD - ct % R_MOD
+
+
+def expected_proof_dlogs_independent(td: Trapdoor, circ: Circuit, w, r: int, s: int):
+    """dlog(A), dlog(B), dlog(C) of the unique proof for (w, r, s), with the H term taken from the trapdoor as
+    (a(tau) b(tau) - c(tau)) / delta instead of from a computed h: independent of every NTT / witness-map code path
+    (CircomReduction keys only: sum_j h_j H_j = [(ab - c)(tau) / delta] G1)."""
+    assert getattr(td, 'flavour', 'circom') == 'circom'
+    li = circ.num_inputs
+    da = (td.alpha + sum(x * y for x, y in zip(w, td.a_t)) + r * td.delta) % R_MOD
+    db = (td.beta + sum(x * y for x, y in zip(w, td.b_t)) + s * td.delta) % R_MOD
+    hterm = qap_numerator_at_tau(td, circ, w) * pow(td.delta, -1, R_MOD) % R_MOD
+    dc = (sum(x * y for x, y in zip(w[li:], td.l_t)) + hterm + s * da + r * db - r * s % R_MOD * td.delta) % R_MOD
+    return da, db, dc
+
+
 def expected_proof_dlogs(td: Trapdoor, w, h, r: int, s: int, num_inputs: int):
-    """dlog(A), dlog(B), dlog(C) of the unique proof for (w, h, r, s) under this trapdoor."""
+    """dlog(A), dlog(B), dlog(C) of the unique proof for (w, h, r, s) under this trapdoor.  NOTE: takes h as an input,
+    so it checks the MSMs and the assembly but NOT the witness map that produced h; expected_proof_dlogs_independent
+    is the check that does."""
     da = (td.alpha + sum(x * y for x, y in zip(w, td.a_t)) + r * td.delta) % R_MOD
     db = (td.beta + sum(x * y for x, y in zip(w, td.b_t)) + s * td.delta) % R_MOD
     dc = (sum(x * y for x, y in zip(w[num_inputs:], td.l_t)) + sum(x * y for x, y in zip(h, td.h_t))

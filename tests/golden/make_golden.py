@@ -28,9 +28,28 @@ def rust_byte_vec(src, fn_name):
     return [int(x) for x in re.findall(r'\d+', m.group(1))]
 
 
+def deser_key_kat(src):
+    """The reference's largest known-answer test, `fn deser_key` (/root/reference/src/zkey.rs:545-763): every point of
+    test.zkey's IC / A / B1 / B2 / L / H queries as the raw bytes it feeds to deserialize_g1 / deserialize_g2.  Extracted
+    by regex from that function's body (not retyped): {field: [[byte, ...] per point]}."""
+    body = re.search(r'fn deser_key\(\) \{(.*?)\n    \}\n', src, re.S).group(1)
+    out, pos = {}, 0
+    for m in re.finditer(r'assert_eq!\(expected, params\.([a-z0-9_.]+)\);', body):
+        chunk, pos = body[pos:m.start()], m.end()
+        pts = []
+        for kind, nums in re.findall(r'deserialize_(g1|g2)\(\s*&mut &\[(.*?)\]\[\.\.\]', chunk, re.S):
+            b = [int(x) for x in re.findall(r'\d+', nums)]
+            assert len(b) == (64 if kind == 'g1' else 128), (m.group(1), len(b))
+            pts.append(b)
+        out[m.group(1).split('.')[-1]] = pts
+    assert {k: len(v) for k, v in out.items()} == {'gamma_abc_g1': 2, 'a_query': 4, 'b_g1_query': 4, 'b_g2_query': 4, 'l_query': 2, 'h_query': 4}
+    return out
+
+
 def main():
     out = {'r': str(R), 's': str(S)}
     src = open(os.path.join(REF, 'src/zkey.rs')).read()
+    out['deser_key'] = deser_key_kat(src)
     out['kat_fq_one'] = rust_byte_vec(src, 'fq_buf')
     out['kat_g1_one'] = rust_byte_vec(src, 'g1_buf')
     out['kat_g2_one'] = rust_byte_vec(src, 'g2_buf')

@@ -111,7 +111,9 @@ def test_fixed_base(ctx):
 
 
 # ------------------------------------------------------------------------------------------------ NTT
-@pytest.mark.parametrize('log_n', [1, 2, 3, 7, 10, 11, 14, 16])
+# 21 / 22: the >= 2^21 pass schedule (three strided pass definitions instead of two, ntt.cu ntt_domain_create) that the
+# 2^22 configuration (BASELINE.json config 4) runs
+@pytest.mark.parametrize('log_n', [1, 2, 3, 7, 10, 11, 14, 16, 20, 21, 22])
 def test_ntt_plain(ctx, log_n):
     rng = np.random.default_rng(log_n)
     n = 1 << log_n
@@ -266,6 +268,8 @@ def test_synthetic_proof_vs_oracle_and_trapdoor(ctx, kind, log_n):
     assert p.data == pb
     da, db, dc = synth.expected_proof_dlogs(td, w, fr_from_mont(h), r, s, circ.num_inputs)
     assert o.G1.mul(o.G1_GEN, da) == p.a and o.G2.mul(o.G2_GEN, db) == p.b and o.G1.mul(o.G1_GEN, dc) == p.c
+    # and the form that takes no h at all: H term = (a(tau) b(tau) - c(tau)) / delta straight from the trapdoor
+    assert synth.expected_proof_dlogs_independent(td, circ, w, r, s) == (da, db, dc)
 
 
 def test_sharded_proof_equals_whole_proof(golden, complex_zkey_bytes):
@@ -369,13 +373,61 @@ def test_headline_2p20_proof_closed_form(ctx):
     r, s = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
     h = CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wm, ctx)
     p = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, circ.num_inputs, circ.num_constraints, wm, ctx)
-    da, db, dc = synth.expected_proof_dlogs(td, w, fr_from_mont(h), r, s, circ.num_inputs)
+    # (1) the witness map against the CPU oracle, bit for bit, at the headline size
+    assert np.array_equal(h, c.witness_map(cm.num_constraints, circ.num_inputs, circ.n_vars, cm.a, cm.b, wm))
+    # (2) the proof against the trapdoor closed form that uses NO h (H term = (a(tau) b(tau) - c(tau)) / delta): a wrong h
+    #     cannot move this expectation.  (3) the h-based form must agree with it (checks h . h_t == the same quantity).
+    da, db, dc = synth.expected_proof_dlogs_independent(td, circ, w, r, s)
+    assert synth.expected_proof_dlogs(td, w, fr_from_mont(h), r, s, circ.num_inputs) == (da, db, dc)
+    _assert_proof_is(p, da, db, dc)
+    release(pk); release(cm)
+
+
+def _assert_proof_is(p, da, db, dc):
     ea = c.limbs_to_ints(c.fq_from_mont(c.fixed_base_g1(c.ints_to_limbs([da, dc]))))
     eb = c.limbs_to_ints(c.fq_from_mont(c.fixed_base_g2(c.ints_to_limbs([db]))))
     assert p.a == (ea[0], ea[1]) and p.c == (ea[2], ea[3]) and p.b == ((eb[0], eb[1]), (eb[2], eb[3]))
-    # the witness map at this size also satisfies the defining identity at a random point is covered by the closed form:
-    # C's dlog contains (ab - c)(tau) through sum h_j * h_t[j]
-    release(pk); release(cm)
+
+
+@pytest.fixture(scope='module')
+def chain22():
+    from circom_compat_b200 import fr_to_mont, synth
+    circ = synth.chain_circuit(1 << 22); w = synth.chain_witness(1 << 22)
+    return circ, w, circ.matrices(), fr_to_mont(w)
+
+
+def test_witness_map_2p22_vs_oracle(ctx, chain22):
+    # BASELINE.json config 4's domain: qap.rs:23-88 on 2^22 rows (the three-pass NTT schedule), bit-exact vs oracle/cref.c
+    from circom_compat_b200 import CircomReduction, release
+    circ, w, cm, wm = chain22
+    h = CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    assert np.array_equal(h, c.witness_map(cm.num_constraints, circ.num_inputs, circ.n_vars, cm.a, cm.b, wm))
+    release(cm)
+
+
+def test_config4_2p22_base_sharded_proof_closed_form(chain22):
+    # BASELINE.json config 4: 2^22-constraint chain, MSM bases sharded by range over every visible GPU (at least two
+    # shard contexts; both on GPU 0 when the box has one), 768-byte partials folded in rank order.  Expected proof =
+    # trapdoor closed form that does not use h (benches/groth16.rs:69-84 shape, qap.rs:30-32 domain rule).
+    import torch
+    from circom_compat_b200 import Groth16, Context, synth, release_all
+    circ, w, cm, wm = chain22
+    ngpu = max(1, torch.cuda.device_count())
+    shards = max(2, ngpu)
+    setup_ctx = Context(0)
+    pk, td = synth.setup(setup_ctx, circ)
+    setup_ctx.close()
+    r, s = 0x1234567890abcdef1234567890abcdef, 0xfedcba0987654321fedcba0987654321
+    parts, ctxs = [], []
+    for rank in range(shards):
+        cx = Context(rank % ngpu, rank, shards); ctxs.append(cx)
+        parts.append(Groth16.prove_partial(pk, cm, wm, cx, r, s))
+    p = Groth16.prove_finish(pk, np.stack(parts), r, s, ctxs[0])
+    assert Groth16.prove_finish(pk, np.stack(parts), r, s, ctxs[-1]).data == p.data      # every rank obtains the same bytes
+    _assert_proof_is(p, *synth.expected_proof_dlogs_independent(td, circ, w, r, s))
+    release_all()
+    for cx in ctxs:
+        cx.close()
 
 
 def test_gpu_setup_prove_verify_flow(ctx):

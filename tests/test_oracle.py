@@ -27,6 +27,38 @@ def test_kat_field_and_generators(golden):
     assert c.limbs_to_ints(g1) == [1, 2]
 
 
+def test_deser_key_kat_every_reader(golden, test_zkey_bytes):
+    """`fn deser_key` (/root/reference/src/zkey.rs:545-763): all 20 points of test.zkey's IC / A / B1 / B2 / L / H queries as
+    the reference pins them (bytes extracted from that test by tests/golden/make_golden.py).  Checked against all three
+    readers of this repository: the oracle's (pyref.read_zkey), the product's Python reader (zkey.read_zkey) and the
+    product's C++ reader (ark_circom::read_zkey, via groth16_bench --parse-only --dump-key)."""
+    import os, re, subprocess
+    from circom_compat_b200 import read_zkey
+    kat = golden['deser_key']
+    assert sum(len(v) for v in kat.values()) == 20
+    z = o.read_zkey(test_zkey_bytes)
+    pk, _ = read_zkey(test_zkey_bytes)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([os.path.join(root, 'circom_compat_b200', 'host', 'groth16_bench'), '--parse-only',
+                                   os.path.join(root, 'tests', 'golden', 'test.zkey'), '--dump-key'], text=True)
+    cpp = {}
+    for name, idx, hx in re.findall(r'^(\w+)\[(\d+)\]=([0-9a-f]+)$', out, re.M):
+        cpp.setdefault(name, []).append(bytes.fromhex(hx))
+    oracle_fields = {'gamma_abc_g1': z.ic, 'a_query': z.a_query, 'b_g1_query': z.b_g1_query, 'b_g2_query': z.b_g2_query,
+                     'l_query': z.l_query, 'h_query': z.h_query}
+    for name, pts in kat.items():
+        g2 = name == 'b_g2_query'
+        exp = [bytes(b) for b in pts]
+        # oracle: decoded affine points (None = infinity, on-curve checked like G1Affine::new) equal the decoded KAT bytes
+        assert oracle_fields[name] == [(o._g2_from(b) if g2 else o._g1_from(b)) for b in exp], name
+        # product readers keep the zkey's Montgomery bytes verbatim (= arkworks' in-memory Fp256 limbs)
+        arr = np.ascontiguousarray(getattr(pk, name))
+        assert [arr[i].tobytes() for i in range(arr.shape[0])] == exp, name
+        assert cpp[name] == exp, name
+    # the points at infinity the reference pins (a_query[3], b_g1_query[0..2], ...) decode to identity in the oracle
+    assert z.a_query[3] is None and z.b_g1_query[:3] == [None, None, None]
+
+
 def test_zkey_header_and_sections(test_zkey_bytes):
     # src/zkey.rs:519-543: n_vars = 4, n_public = 1, domain_size = 4; section sizes
     z = o.read_zkey(test_zkey_bytes)
