@@ -202,97 +202,6 @@ __global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kerne
     }
 }
 
-#ifdef B2G_ENABLE_FP64_ACC
-}  // namespace b2g
-#ifndef B2G52_FQ2_CALL
-#define B2G52_FQ2_CALL __noinline__
-#endif
-#include "../../experiments/dfma/accumulate52.cuh"
-namespace b2g {
-// (4b) experiments/dfma, UNMEASURED, compiled only with -DB2G_ENABLE_FP64_ACC: threads [t_begin, t_end) of the same run
-// list on the FP64 pipe (DFMA + integer adds instead of IMAD.WIDE); see experiments/dfma/README.md.
-// PERSISTENT: a small grid (a fixed number of CTAs per SM) pulls 128-run blocks from a counter, so that its CTAs stay
-// resident next to the integer kernel's for the whole accumulation - two large ordinary grids would simply run one after
-// the other, and the two multiplier pipes would never be busy together.
-__global__ void __launch_bounds__(128, 4) msm_accumulate52_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
-                                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk, void* __restrict__ buckets,
-                                      void* __restrict__ frag_first, void* __restrict__ frag_last, uint32_t t_begin, uint32_t t_end,
-                                      uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count, uint32_t* __restrict__ work_counter) {
-    __shared__ uint32_t blk_sh;
-    const uint32_t nblk = (t_end - t_begin + 127u) / 128u;
-    for (;;) {
-        if (threadIdx.x == 0) blk_sh = atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const uint32_t blk = blk_sh;
-        __syncthreads();
-        if (blk >= nblk) return;
-        const uint32_t t = t_begin + blk * 128u + threadIdx.x;
-        if (t < t_end)
-            b2g52::accumulate52_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
-                                    [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
-    }
-}
-// G2 counterpart (3 CTAs per SM like the integer G2 kernel; the Fq2 wide sums are calls: -DB2G52_FQ2_CALL=__noinline__)
-__global__ void __launch_bounds__(128, 2) msm_accumulate52_g2_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
-                                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk, void* __restrict__ buckets,
-                                      void* __restrict__ frag_first, void* __restrict__ frag_last, uint32_t t_begin, uint32_t t_end,
-                                      uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count, uint32_t* __restrict__ work_counter) {
-    __shared__ uint32_t blk_sh;
-    const uint32_t nblk = (t_end - t_begin + 127u) / 128u;
-    for (;;) {
-        if (threadIdx.x == 0) blk_sh = atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const uint32_t blk = blk_sh;
-        __syncthreads();
-        if (blk >= nblk) return;
-        const uint32_t t = t_begin + blk * 128u + threadIdx.x;
-        if (t < t_end)
-            b2g52::accumulate52_g2_run(t, table, entries, offsets, nb, chunk, buckets, frag_first, frag_last, redo_list, redo_count,
-                                       [](uint32_t* v) { fe r; for (int i = 0; i < 8; i++) r.l[i] = v[i]; r = Fq::reduce_once(r); for (int i = 0; i < 8; i++) v[i] = r.l[i]; });
-    }
-}
-// runs handed back by the FP64 kernel, replayed with the complete addition law (same body as msm_accumulate_kernel)
-template <class C, class F>
-__global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_redo_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
-                                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
-                                      void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last,
-                                      const uint32_t* __restrict__ redo_list, const uint32_t* __restrict__ redo_count) {
-    using Pt = typename C::Pt; using Aff = typename C::Aff;
-    const uint32_t total = offsets[nb], nredo = *redo_count;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nredo; idx += gridDim.x * blockDim.x) {
-        const uint32_t t = redo_list[idx];
-        const uint64_t start64 = (uint64_t)t * chunk;
-        if (start64 >= total) continue;
-        const uint32_t start = (uint32_t)start64;
-        const uint32_t end = (uint32_t)min((uint64_t)total, start64 + chunk);
-        uint32_t lo = 0, hi = nb;
-        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= start) lo = mid; else hi = mid; }
-        uint32_t b = lo;
-        uint32_t bucket_end = offsets[b + 1];
-        while (bucket_end <= start) { b++; bucket_end = offsets[b + 1]; }
-        Pt acc = C::infinity();
-        uint32_t seg_start = start;
-        for (uint32_t pos = start; pos < end;) {
-            uint32_t e = entries[pos];
-            Aff p = aff_load<F>(table, (size_t)(e & 0x7fffffffu));
-            if (e >> 31) p.y = F::neg(p.y);
-            C::madd(acc, p);
-            pos++;
-            if (pos == bucket_end || pos == end) {
-                const uint32_t bucket_start = offsets[b];
-                if (bucket_start >= start && bucket_end <= end) pt_store<F>(buckets, b, acc);
-                else if (seg_start == start) pt_store<F>(frag_first, t, acc);
-                else pt_store<F>(frag_last, t, acc);
-                acc = C::infinity();
-                seg_start = pos;
-                if (pos == bucket_end && pos < end) {
-                    do { b++; bucket_end = offsets[b + 1]; } while (bucket_end <= pos);
-                }
-            }
-        }
-    }
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------ (5) fold fragments
 template <class C, class F>
@@ -458,18 +367,6 @@ void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, b
     CUDA_CHECK(cudaMalloc(&s.buckets, (size_t)nbuckets * pt));
     CUDA_CHECK(cudaMalloc(&s.partials, (npart + 1) * pt));
     CUDA_CHECK(cudaMalloc(&s.result, pt)); s.result_owned = true;
-#ifdef B2G_ENABLE_FP64_ACC
-    s.fp64_share = env_u32(g2 ? "B2G_MSM_FP64_SHARE_G2" : "B2G_MSM_FP64_SHARE", 0);
-    if (s.fp64_share > 100) s.fp64_share = 100;
-    if (s.fp64_share) {
-        CUDA_CHECK(cudaMalloc(&s.redo_list, nchunks * 4));
-        CUDA_CHECK(cudaMalloc(&s.redo_count, 8));           // [0] replay count, [1] work counter of the persistent FP64 grid
-        { int least = 0, greatest = 0; CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-          CUDA_CHECK(cudaStreamCreateWithPriority(&s.fp64, cudaStreamNonBlocking, greatest)); }   // its few persistent CTAs are placed first
-        CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
-    }
-#endif
     if (env_u32("B2G_MSM_TAIL_PRIORITY", 1) == 1) {
         // the tail kernels occupy a handful of CTAs for a long dependent chain: let them be dispatched ahead of the
         // thousands of pending accumulation CTAs of the other queries
@@ -486,9 +383,6 @@ void msm_scratch_free(MsmScratch& s) {
                     s.buckets, s.partials, s.result_owned ? s.result : nullptr, s.scalars_canon};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.tail) { cudaStreamDestroy(s.tail); cudaEventDestroy(s.ev_acc); cudaEventDestroy(s.ev_tail); }
-#ifdef B2G_ENABLE_FP64_ACC
-    if (s.fp64) { cudaStreamDestroy(s.fp64); cudaEventDestroy(s.ev_fork); cudaEventDestroy(s.ev_join); cudaFree(s.redo_list); cudaFree(s.redo_count); }
-#endif
     s = MsmScratch();
 }
 
@@ -521,30 +415,6 @@ static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmS
     const uint64_t nent = (uint64_t)n * plan.nwin;
     const uint32_t nthreads = (uint32_t)((nent + chunk - 1) / chunk);
     if (s.prof0) CUDA_CHECK(cudaEventRecord(s.prof0, st));
-#ifdef B2G_ENABLE_FP64_ACC
-    uint32_t n_int = nthreads;
-    if (s.fp64) {
-        // runs [n_int, nthreads) go to the FP64-pipe kernel on its own stream; both kernels are resident together
-        n_int = (uint32_t)((uint64_t)nthreads * (100 - s.fp64_share) / 100) & ~127u;
-        CUDA_CHECK(cudaMemsetAsync(s.redo_count, 0, 8, st));
-        CUDA_CHECK(cudaEventRecord(s.ev_fork, st));
-        CUDA_CHECK(cudaStreamWaitEvent(s.fp64, s.ev_fork, 0));
-        static int sm_count = 0;
-        if (!sm_count) { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)); }
-        const uint32_t want = (uint32_t)sm_count * env_u32(plan.g2 ? "B2G_MSM_FP64_CTAS_G2" : "B2G_MSM_FP64_CTAS", plan.g2 ? 1 : 2), have = (nthreads - n_int + 127) / 128;
-        if (plan.g2)
-            msm_accumulate52_g2_kernel<<<want < have ? want : have, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
-                                                                                      n_int, nthreads, s.redo_list, s.redo_count, s.redo_count + 1);
-        else
-            msm_accumulate52_kernel<<<want < have ? want : have, 128, 0, s.fp64>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last,
-                                                                                   n_int, nthreads, s.redo_list, s.redo_count, s.redo_count + 1);
-        CUDA_CHECK(cudaEventRecord(s.ev_join, s.fp64));
-        if (n_int) msm_accumulate_kernel<C, F><<<n_int / 128, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
-        CUDA_CHECK(cudaStreamWaitEvent(st, s.ev_join, 0));
-        msm_accumulate_redo_kernel<C, F><<<32, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last, s.redo_list, s.redo_count);
-        g_launch_count += 2;
-    } else
-#endif
     msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
     if (s.prof1) CUDA_CHECK(cudaEventRecord(s.prof1, st));
     cudaStream_t main_st = st;

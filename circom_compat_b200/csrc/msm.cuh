@@ -41,13 +41,6 @@ struct MsmScratch {                      // one per in-flight MSM
     cudaEvent_t prof0 = nullptr, prof1 = nullptr;   // optional: bracket the accumulate kernel (b2g_bench_msm)
     cudaStream_t tail = nullptr;                     // high-priority stream for the low-parallelism fold / weighted-sum kernels
     cudaEvent_t ev_acc = nullptr, ev_tail = nullptr;
-#ifdef B2G_ENABLE_FP64_ACC
-    // experiments/dfma (unmeasured): part of the G1 run list is accumulated by an FP64-pipe kernel on its own stream
-    uint32_t fp64_share = 0;                         // percent of the runs given to the FP64 kernel (B2G_MSM_FP64_SHARE)
-    uint32_t *redo_list = nullptr, *redo_count = nullptr;   // runs the FP64 kernel hands back (equal x-coordinates)
-    cudaStream_t fp64 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-#endif
 };
 
 inline int msm_pick_c(uint32_t n) {

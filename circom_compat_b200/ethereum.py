@@ -107,9 +107,10 @@ def _g1_bytes(p: G1, compressed: bool) -> bytes:
         b = bytearray(p.x.to_bytes(32, 'little'))
         b[31] |= FLAG_INF if inf else (FLAG_NEG if _fq_is_neg(p.y) else 0)
         return bytes(b)
+    # Compress::No: x plain, then y.serialize_with_flags(item.to_flags()) - ark-ec 0.5 writes the YIsNegative bit on y
+    # here too (short_weierstrass SWCurveConfig::serialize_with_mode), not only the infinity flag
     b = bytearray(p.x.to_bytes(32, 'little') + p.y.to_bytes(32, 'little'))
-    if inf:
-        b[63] |= FLAG_INF
+    b[63] |= FLAG_INF if inf else (FLAG_NEG if _fq_is_neg(p.y) else 0)
     return bytes(b)
 
 
@@ -121,8 +122,7 @@ def _g2_bytes(p: G2, compressed: bool) -> bytes:
         b[63] |= FLAG_INF if inf else (FLAG_NEG if _fq2_is_neg(p.y) else 0)
         return bytes(b)
     b = bytearray(xb + p.y[0].to_bytes(32, 'little') + p.y[1].to_bytes(32, 'little'))
-    if inf:
-        b[127] |= FLAG_INF
+    b[127] |= FLAG_INF if inf else (FLAG_NEG if _fq2_is_neg(p.y) else 0)      # flags ride on the last byte of y.c1
     return bytes(b)
 
 
@@ -132,5 +132,7 @@ def serialize_compressed(proof: Proof) -> bytes:
 
 
 def serialize_uncompressed(proof: Proof) -> bytes:
-    """Proof<Bn254>::serialize_uncompressed: 64 + 128 + 64 = 256 bytes"""
+    """Proof<Bn254>::serialize_uncompressed: 64 + 128 + 64 = 256 bytes.  Each point is x || y with the SWFlags of the
+    point (bit 7 = y is the larger of {y, -y}, bit 6 = infinity) OR-ed into the last byte of y, exactly as in the
+    compressed form they ride on x; clear the top two bits of bytes 63 / 191 / 255 to recover the raw coordinates."""
     return _g1_bytes(proof.a, False) + _g2_bytes(proof.b, False) + _g1_bytes(proof.c, False)

@@ -150,7 +150,17 @@ def test_proof_formats(golden, test_zkey_bytes):
     assert len(comp) == 128
     assert o.decompress_proof(comp) == (p.a, p.b, p.c)
     unc = eth.serialize_uncompressed(ep)
-    assert len(unc) == 256 and unc == p.data                               # no point at infinity: identical to the ABI bytes
+    # ark-serialize Compress::No = x || y.serialize_with_flags(to_flags()): the YIsNegative bit (0x80) is set on the last byte
+    # of y (y.c1 for G2) whenever y > -y, so the bytes equal the ABI's raw coordinates only after masking the flag bits
+    assert len(unc) == 256
+    raw = bytearray(unc)
+    for last, neg in ((63, p.a[1] > o.Q_MOD - p.a[1]), (191, (p.b[1][1], p.b[1][0]) > ((o.Q_MOD - p.b[1][1]) % o.Q_MOD, (o.Q_MOD - p.b[1][0]) % o.Q_MOD)),
+                      (255, p.c[1] > o.Q_MOD - p.c[1])):
+        assert (raw[last] & 0xC0) == (0x80 if neg else 0), last
+        raw[last] &= 0x3F
+    assert bytes(raw) == p.data
+    # the flag agrees with the compressed form's (same to_flags() value on x there)
+    assert (unc[63] & 0x80) == (comp[31] & 0x80) and (unc[191] & 0x80) == (comp[95] & 0x80) and (unc[255] & 0x80) == (comp[127] & 0x80)
     inf = eth.Proof(eth.G1(0, 0), ep.b, ep.c)
     assert eth.serialize_compressed(inf)[31] == 0x40 and eth.serialize_uncompressed(inf)[63] == 0x40
     pk, _ = read_zkey(test_zkey_bytes)
