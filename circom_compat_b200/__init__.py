@@ -8,4 +8,5 @@ from .zkey import read_zkey, ProvingKey, ConstraintMatrices, fr_to_mont, fr_from
 from .groth16 import Groth16, CircomReduction, LibsnarkReduction, Proof, Context, release, release_all  # noqa: F401
 from .r1cs import R1CSFile, R1CS, read_wtns  # noqa: F401
 from .builder import CircomConfig, CircomBuilder, CircomCircuit  # noqa: F401
+from .verifier import VerifyingKey, PreparedVerifyingKey, MalformedVerifyingKey  # noqa: F401
 from ._native import B2gError, PolynomialDegreeTooLarge  # noqa: F401

@@ -316,24 +316,35 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
     return x > 0 ? (uint32_t)x : dflt;
 }
 
+// reference behaviour: an off-curve point in a zkey makes G1Affine::new / G2Affine::new panic (src/zkey.rs:340-360); here
+// the load fails with B2G_E_INPUT.  `what` names the points in the message.
+void msm_validate_points(const void* pts_dev, uint32_t n, bool g2, cudaStream_t st, const char* what) {
+    if (n == 0) return;
+    struct Flag { uint32_t* d = nullptr; ~Flag() { if (d) cudaFree(d); } } flag;
+    uint32_t bad = 0;
+    CUDA_CHECK(cudaMalloc(&flag.d, 4));
+    CUDA_CHECK(cudaMemsetAsync(flag.d, 0, 4, st));
+    if (g2) msm_validate_kernel<G2, Fq2><<<(n + 255) / 256, 256, 0, st>>>(pts_dev, n, flag.d);
+    else msm_validate_kernel<G1, Fq><<<(n + 255) / 256, 256, 0, st>>>(pts_dev, n, flag.d);
+    g_launch_count += 1;
+    CUDA_CHECK(cudaMemcpyAsync(&bad, flag.d, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (bad) throw_error(B2G_E_INPUT, std::string(g2 ? "G2" : "G1") + " point " + std::to_string(bad - 1) + " of " + what + " is not on the curve");
+}
+
 template <class C, class F>
 static void msm_build_table_t(MsmPlan& plan, const void* bases_dev, uint32_t n, cudaStream_t st) {
     const size_t aff = 2 * Bytes<F>::ELEM;
-    plan.n = n; plan.c = (int)env_u32("B2G_MSM_C", (uint32_t)msm_pick_c(n ? n : 1)); plan.nwin = msm_nwin(plan.c); plan.nbuckets = 1u << (plan.c - 1);
+    // B2G_MSM_C is a tuning override; outside [8, 22] the window count would overflow MSM_MAX_WIN or the bucket count 2^31
+    uint32_t c = env_u32("B2G_MSM_C", (uint32_t)msm_pick_c(n ? n : 1));
+    if (c < 8 || c > 22) throw_error(B2G_E_SHAPE, "B2G_MSM_C must be in [8, 22]");
+    plan.n = n; plan.c = (int)c; plan.nwin = msm_nwin(plan.c); plan.nbuckets = 1u << (plan.c - 1);
     if (n == 0) { plan.table = nullptr; return; }
     if ((uint64_t)n * plan.nwin >= (1ull << 31)) throw_error(B2G_E_SHAPE, "msm: n * windows exceeds 2^31 table rows");
-    // reference behaviour: an off-curve point in a zkey makes G1Affine::new panic (src/zkey.rs:347); here: B2G_E_INPUT
-    uint32_t* d_bad = nullptr; uint32_t bad = 0;
-    CUDA_CHECK(cudaMalloc(&d_bad, 4));
-    CUDA_CHECK(cudaMemsetAsync(d_bad, 0, 4, st));
-    msm_validate_kernel<C, F><<<(n + 255) / 256, 256, 0, st>>>(bases_dev, n, d_bad);
-    CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(d_bad);
-    if (bad) throw_error(B2G_E_INPUT, std::string(plan.g2 ? "G2" : "G1") + " base " + std::to_string(bad - 1) + " of the query slice is not on the curve");
+    msm_validate_points(bases_dev, n, plan.g2, st, "the query slice");
     CUDA_CHECK(cudaMalloc(&plan.table, (size_t)n * plan.nwin * aff));
     msm_table_kernel<C, F><<<(n + 127) / 128, 128, 0, st>>>(bases_dev, n, plan.c, plan.nwin, plan.table);
-    g_launch_count += 2;
+    g_launch_count += 1;
     CUDA_CHECK(cudaGetLastError());
 }
 

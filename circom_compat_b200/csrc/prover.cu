@@ -25,6 +25,7 @@ void msm_accumulate(const MsmPlan& plan, const MsmScratch& sorted, MsmScratch& a
 void msm_scratch_free(MsmScratch& s);
 void msm_run(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_t n, bool scalars_mont, cudaStream_t st);
 void msm_init_kernels();
+void msm_validate_points(const void* pts_dev, uint32_t n, bool g2, cudaStream_t st, const char* what);
 
 enum { Q_H = 0, Q_L = 1, Q_A = 2, Q_B1 = 3, Q_B2 = 4, NQ = 5 };
 static const size_t PARTIAL_OFF[NQ] = {0, 128, 256, 384, 512};
@@ -398,10 +399,17 @@ static void run_witness_map(b2g_ctx* ctx, b2g_mat* mat, cudaStream_t st) {
     ntt_witness_transform(mat->dom, ctx->d_a, ctx->d_b, ctx->d_c, ctx->d_h, st);
 }
 
+// a key's tables live on one device and describe one shard: checked before the first kernel that dereferences them
+static void check_pk_ctx(const b2g_ctx* ctx, const b2g_pk* pk) {
+    if (!ctx || !pk) throw_error(B2G_E_SHAPE, "null handle");
+    if (pk->device != ctx->device) throw_error(B2G_E_SHAPE, "handle belongs to another device");
+    if (pk->shard_rank != ctx->shard_rank || pk->shard_count != ctx->shard_count) throw_error(B2G_E_SHAPE, "proving key was loaded for another shard");
+}
+
 static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
     if (!ctx || !pk || !mat) throw_error(B2G_E_SHAPE, "null handle");
-    if (pk->device != ctx->device || mat->device != ctx->device) throw_error(B2G_E_SHAPE, "handle belongs to another device");
-    if (pk->shard_rank != ctx->shard_rank || pk->shard_count != ctx->shard_count) throw_error(B2G_E_SHAPE, "proving key was loaded for another shard");
+    check_pk_ctx(ctx, pk);
+    if (mat->device != ctx->device) throw_error(B2G_E_SHAPE, "handle belongs to another device");
     if (pk->n_vars != mat->n_vars) throw_error(B2G_E_SHAPE, "proving key and matrices disagree on n_vars");
     if (mat->reduction == B2G_REDUCTION_LIBSNARK) {
         // arkworks keys carry domain - 1 H bases; msm_bigint pairs min(len) terms (the top coefficient of h is zero)
@@ -434,6 +442,15 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
     msm_run(pk->plan[Q_H], ctx->scratch[Q_H], ctx->d_h + pk->lo[Q_H], pk->cnt[Q_H], true, s0);   // pairs min(#bases, #h) terms
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[1], s0));
     for (int q = 1; q < NQ; q++) CUDA_CHECK(cudaStreamWaitEvent(s0, ctx->ev_done[q], 0));
+}
+
+// frees every device allocation of a (possibly partially built) key and the key itself
+static void pk_release(b2g_pk* pk) {
+    for (int q = 0; q < NQ; q++) msm_free_table(pk->plan[q]);
+    if (pk->d_consts) cudaFree(pk->d_consts);
+    if (pk->d_tab_delta1) cudaFree(pk->d_tab_delta1);
+    if (pk->d_tab_delta2) cudaFree(pk->d_tab_delta2);
+    delete pk;
 }
 
 static Scalar256 load_scalar(const void* p) { Scalar256 s; memcpy(s.l, p, 32); return s; }
@@ -531,7 +548,12 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
             if (!p) throw_error(B2G_E_SHAPE, "null proving-key section");
         DevGuard g(ctx->device);
         cudaStream_t st = ctx->st[0];
-        b2g_pk* pk = new b2g_pk();
+        // everything allocated below is released if any later step throws (off-curve point, out of memory, ...)
+        struct PkGuard {
+            b2g_pk* pk = new b2g_pk(); void* tmp = nullptr;
+            ~PkGuard() { if (tmp) cudaFree(tmp); if (pk) pk_release(pk); }
+        } guard;
+        b2g_pk* pk = guard.pk;
         pk->device = ctx->device; pk->shard_rank = ctx->shard_rank; pk->shard_count = ctx->shard_count; pk->n_vars = d->n_vars; pk->n_public = d->n_public; pk->domain = d->domain_size;
         const uint32_t li = d->n_public + 1;
         // query sizes as paired with scalars by create_proof_with_assignment
@@ -552,18 +574,21 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
             pk->cnt[q] = (uint32_t)((uint64_t)total[q] * (r + 1) / R) - pk->lo[q];
             pk->scalar_off[q] = soff[q];
             if (total[q] && !src[q]) throw_error(B2G_E_SHAPE, "null proving-key section");
-            void* tmp = nullptr;
-            if (pk->cnt[q]) tmp = dev_upload<uint8_t>((const uint8_t*)src[q] + (size_t)(base_skip[q] + pk->lo[q]) * aff, (size_t)pk->cnt[q] * aff, st);
-            msm_build_table(pk->plan[q], tmp, pk->cnt[q], g2, st);
+            if (pk->cnt[q]) guard.tmp = dev_upload<uint8_t>((const uint8_t*)src[q] + (size_t)(base_skip[q] + pk->lo[q]) * aff, (size_t)pk->cnt[q] * aff, st);
+            msm_build_table(pk->plan[q], guard.tmp, pk->cnt[q], g2, st);
             g_launch_count += 1;
             CUDA_CHECK(cudaStreamSynchronize(st));
-            if (tmp) cudaFree(tmp);
+            if (guard.tmp) { cudaFree(guard.tmp); guard.tmp = nullptr; }
         }
         std::vector<uint8_t> consts(5 * 64 + 3 * 128);
         memcpy(&consts[0], d->alpha_g1, 64); memcpy(&consts[64], d->beta_g1, 64); memcpy(&consts[128], d->delta_g1, 64);
         memcpy(&consts[192], d->a_query, 64); memcpy(&consts[256], d->b_g1_query, 64);
         memcpy(&consts[320], d->beta_g2, 128); memcpy(&consts[448], d->delta_g2, 128); memcpy(&consts[576], d->b_g2_query, 128);
         pk->d_consts = dev_upload<uint8_t>(consts.data(), consts.size(), st);
+        // alpha, beta, delta and the three query[0] points never pass through a table build: G1Affine::new / G2Affine::new
+        // validate them in the reference (src/zkey.rs:340-360), so they are checked here as well
+        msm_validate_points(pk->d_consts, 5, false, st, "alpha_g1 / beta_g1 / delta_g1 / a_query[0] / b_g1_query[0]");
+        msm_validate_points(pk->d_consts + 5 * 64, 3, true, st, "beta_g2 / delta_g2 / b_g2_query[0]");
         CUDA_CHECK(cudaMalloc(&pk->d_tab_delta1, 32 * 255 * 64));
         CUDA_CHECK(cudaMalloc(&pk->d_tab_delta2, 32 * 255 * 128));
         fixed_table_kernel<G1, Fq><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_delta1, pk->d_consts + 2 * 64);
@@ -571,6 +596,7 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
         g_launch_count += 2;
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaStreamSynchronize(st));
+        guard.pk = nullptr;
         *out = pk;
     });
 }
@@ -580,11 +606,7 @@ int b2g_pk_free(b2g_pk* pk) {
         if (!pk) return;
         DevGuard g(pk->device);
         cudaDeviceSynchronize();
-        for (int q = 0; q < NQ; q++) msm_free_table(pk->plan[q]);
-        if (pk->d_consts) cudaFree(pk->d_consts);
-        if (pk->d_tab_delta1) cudaFree(pk->d_tab_delta1);
-        if (pk->d_tab_delta2) cudaFree(pk->d_tab_delta2);
-        delete pk;
+        pk_release(pk);
     });
 }
 
@@ -605,6 +627,13 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
         if (libsnark && !d->c_rowptr) throw_error(B2G_E_SHAPE, "LibsnarkReduction needs the C matrix");
         const uint32_t cnnz = libsnark ? d->c_rowptr[m] : 0;
         if (cnnz && (!d->c_col || !d->c_val)) throw_error(B2G_E_SHAPE, "null matrix arrays");
+        // row pointers index col / val on the device: must start at 0 and never decrease (the last one is the nnz used above)
+        auto check_rowptr = [&](const uint32_t* rp, const char* name) {
+            if (rp[0] != 0) throw_error(B2G_E_SHAPE, std::string("matrix ") + name + ": rowptr[0] != 0");
+            for (uint32_t i = 0; i < m; i++) if (rp[i + 1] < rp[i]) throw_error(B2G_E_SHAPE, std::string("matrix ") + name + ": row pointers decrease at row " + std::to_string(i));
+        };
+        check_rowptr(d->a_rowptr, "A"); check_rowptr(d->b_rowptr, "B");
+        if (libsnark) check_rowptr(d->c_rowptr, "C");
         for (uint32_t k = 0; k < cnnz; k++) if (d->c_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix C column index out of range");
         for (uint32_t k = 0; k < annz; k++) if (d->a_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix A column index out of range");
         for (uint32_t k = 0; k < bnnz; k++) if (d->b_col[k] >= d->n_vars) throw_error(B2G_E_SHAPE, "matrix B column index out of range");
@@ -675,7 +704,7 @@ int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const
         if (!ctx || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
         if (ctx->shard_count != 1) throw_error(B2G_E_SHAPE, "b2g_prove needs an unsharded context; use b2g_prove_partial/finish");
         DevGuard g(ctx->device);
-        if (!pk) throw_error(B2G_E_SHAPE, "null handle");
+        check_shapes(ctx, pk, mat);
         launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
         cudaStream_t s0 = ctx->st[0];
@@ -692,6 +721,7 @@ int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_cano
     return guarded([&] {
         if (!ctx || !pk || !partial_out) throw_error(B2G_E_SHAPE, "null pointer");
         DevGuard g(ctx->device);
+        check_shapes(ctx, pk, mat);
         ctx->pre_valid = false;
         if (r_canon && s_canon) launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
@@ -708,6 +738,7 @@ int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int cou
     return guarded([&] {
         if (!ctx || !pk || !partials_all || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
         if (count < 1 || count > 64) throw_error(B2G_E_SHAPE, "partial count out of range");
+        check_pk_ctx(ctx, pk);
         DevGuard g(ctx->device);
         cudaStream_t s0 = ctx->st[0];
         if (!(ctx->pre_valid && !memcmp(ctx->pre_r, r_canon, 32) && !memcmp(ctx->pre_s, s_canon, 32))) launch_glue_pre(ctx, pk, r_canon, s_canon);
@@ -788,6 +819,7 @@ int b2g_prove_sharded_p2p(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_
         if (!ctx || !pk || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
         if (ctx->peers_imported != ctx->shard_count) throw_error(B2G_E_SHAPE, "b2g_p2p_import has not been called with every rank's handle");
         DevGuard g(ctx->device);
+        check_shapes(ctx, pk, mat);
         launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
         cudaStream_t s0 = ctx->st[0];

@@ -219,6 +219,24 @@ def _scalar_bytes(v) -> np.ndarray:
     return a
 
 
+def fr_rand(rng) -> int:
+    """Fr::rand of ark-ff 0.5 (SURVEY.md App. C.5), the rule Groth16::prove uses for r and s: four u64 limbs from the rng
+    (limb 0 first), the top two bits of limb 3 cleared, rejected and redrawn if >= r, and the limbs taken AS the Montgomery
+    representation (value = limbs * R^-1 mod r).  `rng` supplies 64-bit words through next_u64() if it has one (an adapter
+    over a rand-compatible stream), else through getrandbits(64) (random.Random, secrets.SystemRandom).  Same rule as
+    ark_circom::Fr::rand in the C++ mirror."""
+    nxt = rng.next_u64 if hasattr(rng, 'next_u64') else (lambda: rng.getrandbits(64))
+    while True:
+        limbs = [nxt() & 0xFFFFFFFFFFFFFFFF for _ in range(4)]
+        limbs[3] &= 0x3FFFFFFFFFFFFFFF
+        v = sum(x << (64 * i) for i, x in enumerate(limbs))
+        if v < R_MOD:
+            return v * _R_INV_R % R_MOD
+
+
+_R_INV_R = pow(1 << 256, -1, R_MOD)
+
+
 class CircomReduction:
     """R1CSToQAP implementation selected by Groth16<Bn254, CircomReduction> (src/circom/qap.rs:12-14)."""
     ID = N.REDUCTION_CIRCOM
@@ -267,11 +285,10 @@ class Groth16:
 
     @staticmethod
     def prove(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, rng, ctx: Context = None, reduction=CircomReduction) -> Proof:
-        """Draws r then s like create_random_proof_with_reduction (ark-groth16 0.5.0); rng is any object with
-        randrange (e.g. random.Random / secrets.SystemRandom).  NB: arkworks' Fr::rand interprets the sampled limbs
-        as a Montgomery residue; the distribution is uniform either way."""
-        r = rng.randrange(R_MOD)
-        s = rng.randrange(R_MOD)
+        """Draws r then s like create_random_proof_with_reduction (ark-groth16 0.5.0), each with the Fr::rand limb rule
+        (fr_rand above): fed the same u64 stream as a seeded arkworks rng, it proves with the same (r, s)."""
+        r = fr_rand(rng)
+        s = fr_rand(rng)
         return Groth16.create_proof_with_reduction_and_matrices(pk, r, s, matrices, matrices.num_instance_variables,
                                                                 matrices.num_constraints, full_assignment, ctx, reduction)
 
@@ -281,6 +298,25 @@ class Groth16:
         from . import synth
         flavour = 'libsnark' if reduction.ID == N.REDUCTION_LIBSNARK else 'circom'
         return synth.generate_random_parameters_with_reduction(circuit, rng, ctx or default_context(), flavour)
+
+    # ---- verification (host pairing; circom_compat_b200/verifier.py).  Call sites in the reference: src/zkey.rs:868-870,
+    # 914-916 (process_vk + verify_with_processed_vk), tests/groth16.rs:33-35 (SNARK::verify).
+    @staticmethod
+    def process_vk(vk):
+        """Groth16::process_vk(&params.vk): `vk` is a verifier.VerifyingKey or a ProvingKey (its vk part is used)."""
+        from . import verifier
+        return verifier.prepare_verifying_key(vk)
+
+    @staticmethod
+    def verify_with_processed_vk(pvk, public_inputs, proof) -> bool:
+        """public_inputs = w[1..num_inputs] as integers (CircomCircuit::get_public_inputs, src/circom/circuit.rs:18-26)"""
+        from . import verifier
+        return verifier.verify_with_processed_vk(pvk, public_inputs, proof)
+
+    @staticmethod
+    def verify(vk, public_inputs, proof) -> bool:
+        from . import verifier
+        return verifier.verify(vk, public_inputs, proof)
 
     # base-range sharded variant: every rank calls prove_partial, the 768-byte partials are all-gathered by the caller
     # (torch.distributed / NCCL), then every rank calls prove_finish and obtains the same proof.

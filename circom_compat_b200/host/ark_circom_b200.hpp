@@ -8,6 +8,8 @@
 //   ark_circom::CircomReduction::witness_map_from_matrices      <- src/circom/qap.rs:23-88
 //   ark_circom::Groth16::create_proof_with_reduction_and_matrices <- call sites src/zkey.rs:903-912, benches/groth16.rs:52-61
 //   ark_circom::Groth16::prove                         <- src/zkey.rs:866 (draws r then s)
+//   ark_circom::Groth16::process_vk / verify_with_processed_vk / verify <- src/zkey.rs:868-870, tests/groth16.rs:33-35
+//                                                         (host pairing, ark_circom_verifier.hpp; no GPU involved)
 //   ark_circom::read_wtns                              <- snarkjs .wtns (test-vectors/circuit2_js/witness.wtns; the reference
 //                                                         computes witnesses with WASM instead, out of scope here)
 // Parsing and key handling stay on the host; every field/curve operation of the proof runs in libb2groth.so.
@@ -102,11 +104,33 @@ static_assert(sizeof(G1Affine) == 64 && sizeof(G2Affine) == 128, "zkey point lay
 
 struct VerifyingKey { G1Affine alpha_g1; G2Affine beta_g2, gamma_g2, delta_g2; std::vector<G1Affine> gamma_abc_g1; };
 
+// Device copies (fixed-base tables, CSR matrices) belong to the host object they were made from: the slot is a member
+// of ProvingKey / ConstraintMatrices, so the gigabytes of HBM are freed when that object dies, and a copy or an
+// assignment - the ways a *different* key can come to live at the same address - start with an empty slot.  The device
+// copy is a snapshot taken at first use: after mutating a key in place call release_device().
+class DeviceSlot {
+public:
+    DeviceSlot() = default;
+    DeviceSlot(const DeviceSlot&) {}                                   // a copy has no device state of its own yet
+    DeviceSlot(DeviceSlot&& o) noexcept : handles_(std::move(o.handles_)), free_(o.free_) { o.handles_.clear(); }
+    DeviceSlot& operator=(const DeviceSlot&) { release(); return *this; }   // new contents => stale tables must go
+    DeviceSlot& operator=(DeviceSlot&& o) noexcept { if (this != &o) { release(); handles_ = std::move(o.handles_); free_ = o.free_; o.handles_.clear(); } return *this; }
+    ~DeviceSlot() { release(); }
+    void release() const { for (auto& kv : handles_) if (kv.second && free_) free_(kv.second); handles_.clear(); }
+    void* find(const void* ctx, uint32_t tag) const { auto it = handles_.find({ctx, tag}); return it == handles_.end() ? nullptr : it->second; }
+    void put(const void* ctx, uint32_t tag, void* h, void (*free_fn)(void*)) const { handles_[{ctx, tag}] = h; free_ = free_fn; }
+private:
+    mutable std::map<std::pair<const void*, uint32_t>, void*> handles_;       // (b2g_ctx, variant) -> b2g_pk* / b2g_mat*
+    mutable void (*free_)(void*) = nullptr;
+};
+
 struct ProvingKey {                                     // ProvingKey<Bn254>, src/zkey.rs:121-130
     VerifyingKey vk;
     G1Affine beta_g1, delta_g1;
     std::vector<G1Affine> a_query, b_g1_query, h_query, l_query;
     std::vector<G2Affine> b_g2_query;
+    DeviceSlot device;                                  // see DeviceSlot
+    void release_device() const { device.release(); }
 };
 
 typedef std::vector<std::vector<std::pair<Fr, size_t>>> Matrix;     // rows of (coeff, index): src/zkey.rs:168
@@ -115,6 +139,8 @@ struct ConstraintMatrices {                             // src/zkey.rs:181-193
     size_t num_instance_variables = 0, num_witness_variables = 0, num_constraints = 0;
     size_t a_num_non_zero = 0, b_num_non_zero = 0, c_num_non_zero = 0;
     Matrix a, b, c;
+    DeviceSlot device;
+    void release_device() const { device.release(); }
 };
 
 struct Proof {                                          // Proof<Bn254>; coordinates canonical little-endian
@@ -258,35 +284,32 @@ inline std::vector<Fr> read_wtns(std::istream& r) {
 }
 
 // ---------------------------------------------------------------------------------------------- device side
-// One Gpu = one b2g_ctx (one in-flight proof on one device).  Keys / matrices are uploaded once and cached by address.
+// One Gpu = one b2g_ctx (one in-flight proof on one device).  Keys / matrices are uploaded on first use; the handle lives
+// in the host object's DeviceSlot (freed with it), never in an address-keyed table.  A Gpu must outlive the proofs issued
+// on it, not the keys: b2g_pk_free / b2g_matrices_free need only the device.
 class Gpu {
 public:
     explicit Gpu(int device = 0) { check(b2g_ctx_create(device, 0, 1, &ctx_)); }
-    ~Gpu() {
-        for (auto& kv : pks_) b2g_pk_free(kv.second);
-        for (auto& kv : mats_) b2g_matrices_free(kv.second);
-        if (ctx_) b2g_ctx_destroy(ctx_);
-    }
+    ~Gpu() { if (ctx_) b2g_ctx_destroy(ctx_); }
     Gpu(const Gpu&) = delete; Gpu& operator=(const Gpu&) = delete;
     static Gpu& instance() { static Gpu g(0); return g; }
     b2g_ctx* ctx() { return ctx_; }
 
     b2g_pk* pk(const ProvingKey& k) {
-        auto it = pks_.find(&k);
-        if (it != pks_.end()) return it->second;
+        if (void* h = k.device.find(ctx_, 0)) return (b2g_pk*)h;
         b2g_pk_desc d; memset(&d, 0, sizeof d);
         d.n_vars = (uint32_t)k.a_query.size(); d.n_public = (uint32_t)k.vk.gamma_abc_g1.size() - 1; d.domain_size = (uint32_t)k.h_query.size();
         d.alpha_g1 = &k.vk.alpha_g1; d.beta_g1 = &k.beta_g1; d.delta_g1 = &k.delta_g1; d.beta_g2 = &k.vk.beta_g2; d.delta_g2 = &k.vk.delta_g2;
         d.a_query = k.a_query.data(); d.b_g1_query = k.b_g1_query.data(); d.b_g2_query = k.b_g2_query.data();
         d.l_query = k.l_query.data(); d.h_query = k.h_query.data();
         b2g_pk* h = nullptr; check(b2g_pk_load(ctx_, &d, &h));
-        return pks_[&k] = h;
+        k.device.put(ctx_, 0, h, [](void* p) { b2g_pk_free((b2g_pk*)p); });
+        return h;
     }
 
     b2g_mat* mat(const ConstraintMatrices& m, size_t n_vars, uint32_t reduction = B2G_REDUCTION_CIRCOM) {
-        auto key = std::make_pair(&m, reduction);
-        auto it = mats_.find(key);
-        if (it != mats_.end()) return it->second;
+        const uint32_t tag = reduction | (uint32_t)(n_vars << 1);     // a matrices handle is specific to (reduction, n_vars)
+        if (void* h = m.device.find(ctx_, tag)) return (b2g_mat*)h;
         std::vector<uint32_t> rp[3], col[3]; std::vector<Fr> val[3];
         const Matrix* src[3] = {&m.a, &m.b, &m.c};
         const int nmat = reduction == B2G_REDUCTION_LIBSNARK ? 3 : 2;
@@ -305,13 +328,12 @@ public:
         d.b_rowptr = rp[1].data(); d.b_col = col[1].data(); d.b_val = val[1].data();
         if (nmat == 3) { d.c_rowptr = rp[2].data(); d.c_col = col[2].data(); d.c_val = val[2].data(); }
         b2g_mat* h = nullptr; check(b2g_matrices_load(ctx_, &d, &h));
-        return mats_[key] = h;
+        m.device.put(ctx_, tag, h, [](void* p) { b2g_matrices_free((b2g_mat*)p); });
+        return h;
     }
 
 private:
     b2g_ctx* ctx_ = nullptr;
-    std::map<const ProvingKey*, b2g_pk*> pks_;
-    std::map<std::pair<const ConstraintMatrices*, uint32_t>, b2g_mat*> mats_;
 };
 
 template <uint32_t REDUCTION>
@@ -332,8 +354,20 @@ struct Reduction {
 typedef Reduction<B2G_REDUCTION_CIRCOM> CircomReduction;       // src/circom/qap.rs:12-14 (snarkjs keys)
 typedef Reduction<B2G_REDUCTION_LIBSNARK> LibsnarkReduction;   // ark-groth16's default QAP (tests/groth16.rs:9,25-35; needs matrices.c)
 
+}  // namespace ark_circom
+#include "ark_circom_verifier.hpp"
+namespace ark_circom {
+
 template <class QAP = CircomReduction>
 struct Groth16T {                                       // Groth16::<Bn254, QAP>
+    // verification (host pairing, ark_circom_verifier.hpp): src/zkey.rs:868-870, 914-916; tests/groth16.rs:33-35
+    static PreparedVerifyingKey process_vk(const VerifyingKey& vk) { return prepare_verifying_key(vk); }
+    static bool verify_with_processed_vk(const PreparedVerifyingKey& pvk, const std::vector<Fr>& public_inputs, const Proof& proof) {
+        return ark_circom::verify_with_processed_vk(pvk, public_inputs, proof);
+    }
+    static bool verify(const VerifyingKey& vk, const std::vector<Fr>& public_inputs, const Proof& proof) {
+        return ark_circom::verify_with_processed_vk(prepare_verifying_key(vk), public_inputs, proof);
+    }
     static Proof create_proof_with_reduction_and_matrices(const ProvingKey& pk, const Fr& r, const Fr& s, const ConstraintMatrices& matrices,
                                                           size_t num_inputs, size_t num_constraints, const std::vector<Fr>& full_assignment,
                                                           Gpu& gpu = Gpu::instance()) {

@@ -2,6 +2,7 @@
 // draw / take (r, s), call Groth16::create_proof_with_reduction_and_matrices repeatedly and report the time per proof.
 //
 //   groth16_bench --parse-only <circuit.zkey> [--dump-key]         host-only: print what read_zkey produced (no GPU)
+//   groth16_bench --verify <circuit.zkey> <proof_hex> [inputs...]  host-only: process_vk + verify_with_processed_vk
 //   groth16_bench <circuit.zkey> chain:<a>|<witness.wtns> [iters] [r_hex s_hex]
 //       chain:<a> = the witness of the reference's squaring-chain bench family for input a
 //       (test-vectors/complex-circuit/input.json has a = 3), computed on the host instead of by WASM.
@@ -79,6 +80,20 @@ int main(int argc, char** argv) {
             }
             return 0;
         }
+        if (argc >= 4 && std::string(argv[1]) == "--verify") {              // host-only: --verify <zkey> <proof_hex> [public inputs, decimal u64 or 0x hex]
+            std::ifstream f(argv[2], std::ios::binary);
+            if (!f) throw SerializationError("cannot open zkey");
+            auto kv = read_zkey(f);
+            std::string hx = argv[3];
+            if (hx.size() != 512) throw std::invalid_argument("proof must be 256 bytes of hex");
+            Proof proof;
+            for (int i = 0; i < 256; i++) proof.bytes[i] = (uint8_t)std::stoul(hx.substr(2 * i, 2), nullptr, 16);
+            std::vector<Fr> inputs;
+            for (int i = 4; i < argc; i++) { std::string a = argv[i]; inputs.push_back(a.rfind("0x", 0) == 0 ? Fr::from_bigint(parse_hex(a)) : Fr::from_u64(std::stoull(a))); }
+            auto pvk = Groth16::process_vk(kv.first.vk);                    // src/zkey.rs:868
+            std::printf("verified=%d\n", Groth16::verify_with_processed_vk(pvk, inputs, proof) ? 1 : 0);
+            return 0;
+        }
         if (argc < 3) { std::fprintf(stderr, "usage: %s [--parse-only] <zkey> chain:<a>|<wtns> [iters] [r_hex s_hex]\n", argv[0]); return 2; }
         std::ifstream f(argv[1], std::ios::binary);
         if (!f) throw SerializationError("cannot open zkey");
@@ -95,6 +110,11 @@ int main(int argc, char** argv) {
         else { std::mt19937_64 rng(0xB200); r = Fr::rand(rng); s = Fr::rand(rng); }      // benches/groth16.rs:45-50
         Proof proof = Groth16::create_proof_with_reduction_and_matrices(params, r, s, matrices, num_inputs, num_constraints, full_assignment);
         std::printf("proof=%s\n", proof.hex().c_str());
+        {   // src/zkey.rs:868-872: process_vk, public inputs = w[1..num_inputs] (circuit.rs:18-26), verify_with_processed_vk
+            auto pvk = Groth16::process_vk(params.vk);
+            std::vector<Fr> inputs(full_assignment.begin() + 1, full_assignment.begin() + num_inputs);
+            std::printf("verified=%d\n", Groth16::verify_with_processed_vk(pvk, inputs, proof) ? 1 : 0);
+        }
         auto t0 = std::chrono::steady_clock::now();
         for (int i = 0; i < iters; i++)                             // benches/groth16.rs:69-84
             proof = Groth16::create_proof_with_reduction_and_matrices(params, r, s, matrices, num_inputs, num_constraints, full_assignment);

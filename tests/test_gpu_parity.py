@@ -213,6 +213,11 @@ def test_witness_map_and_proofs_test_zkey(ctx, golden, test_zkey_bytes):
                                                              cm.num_constraints, wm, ctx)
         assert p.data.hex() == case['proof_hex'], i
         if i == 0:
+            # src/zkey.rs:868-872: process_vk + verify_with_processed_vk on the product's own host verifier; the oracle's
+            # (differently built) pairing must agree
+            pvk = Groth16.process_vk(pk)
+            assert Groth16.verify_with_processed_vk(pvk, w[1:cm.num_instance_variables], p)
+            assert not Groth16.verify_with_processed_vk(pvk, [34], p)
             assert o.verify(z, w[1:cm.num_instance_variables], (p.a, p.b, p.c))
 
 
@@ -320,7 +325,7 @@ def test_cpp_host_mirror_proves_golden(golden, tmp_path):
     g = golden['complex_zkey']
     out = subprocess.check_output([exe, os.path.join(root, 'tests', 'golden', 'complex-circuit-10000-10000.zkey'), 'chain:%d' % g['a'], '2',
                                    '%x' % int(g['r']), '%x' % int(g['s'])], text=True)
-    assert 'proof=' + g['proof_hex'] in out
+    assert 'proof=' + g['proof_hex'] in out and 'verified=1' in out      # C++ process_vk + verify_with_processed_vk
     gt = golden['test_zkey']
     w = [int(x) for x in gt['witness']]
     wt = tmp_path / 'w.wtns'
@@ -439,14 +444,12 @@ def test_gpu_setup_prove_verify_flow(ctx):
     pk = Groth16.generate_random_parameters_with_reduction(circ, rng, ctx)
     cm = circ.matrices()
     p = Groth16.prove(pk, cm, fr_to_mont(w), rng, ctx)
-    vk = o.ZKey()
-    def g1(a): return o._g1_from(np.ascontiguousarray(a).tobytes())
-    def g2(a): return o._g2_from(np.ascontiguousarray(a).tobytes())
-    vk.alpha_g1, vk.beta_g2, vk.gamma_g2, vk.delta_g2 = g1(pk.alpha_g1), g2(pk.beta_g2), g2(pk.gamma_g2), g2(pk.delta_g2)
-    vk.ic = [g1(x) for x in pk.gamma_abc_g1]
+    vk = _vk_from_pk(pk)
     assert vk.gamma_g2 != o.G2_GEN                                   # gamma is random here, not 1
+    # tests/groth16.rs:33-37: Groth16::verify(&vk, &inputs, &proof) on the product's verifier; oracle pairing as cross-check
+    assert Groth16.verify(pk, w[1:circ.num_inputs], p)
+    assert not Groth16.verify(pk, [(w[1] + 1) % o.R_MOD], p)
     assert o.verify(vk, w[1:circ.num_inputs], (p.a, p.b, p.c))
-    assert not o.verify(vk, [(w[1] + 1) % o.R_MOD], (p.a, p.b, p.c))
     release(pk); release(cm)
 
 
@@ -488,9 +491,10 @@ def test_r1cs_route_setup_prove_verify(ctx):
         assert len(pk.h_query) == circ.domain_size - 1
         wm = fr_to_mont(w)
         p = Groth16.prove(pk, cm, wm, rng, ctx, LibsnarkReduction)
-        vk = _vk_from_pk(pk)
-        assert o.verify(vk, w[1:r.num_inputs], (p.a, p.b, p.c)), r1cs_name
-        assert not o.verify(vk, [(w[1] + 1) % o.R_MOD], (p.a, p.b, p.c))
+        pvk = Groth16.process_vk(pk)
+        assert Groth16.verify_with_processed_vk(pvk, w[1:r.num_inputs], p), r1cs_name
+        assert not Groth16.verify_with_processed_vk(pvk, [(w[1] + 1) % o.R_MOD] + w[2:r.num_inputs], p)
+        assert o.verify(_vk_from_pk(pk), w[1:r.num_inputs], (p.a, p.b, p.c)), r1cs_name
         # the witness map behind it is the oracle's
         h = LibsnarkReduction.witness_map_from_matrices(cm, r.num_inputs, len(r.constraints), wm, ctx)
         ni, nw, cons = r.num_inputs, r.num_variables, [tuple([(v, i) for i, v in lc] for lc in con) for con in r.constraints]

@@ -133,6 +133,72 @@ def test_cpp_read_zkey_matches_python_reader(name):
         assert int(kv['coefs'], 16) == h
 
 
+def test_fr_rand_limb_rule():
+    # limbs from next_u64 (limb 0 first), top two bits cleared, reject >= r, limbs ARE the Montgomery residue
+    from circom_compat_b200.groth16 import fr_rand
+
+    class Stream:
+        def __init__(self, words): self.words = list(words)
+        def next_u64(self): return self.words.pop(0)
+    R = 1 << 256
+    top = o.R_MOD >> 192                                     # limb 3 of r: a draw whose limb 3 exceeds it is rejected
+    rejected = [0, 0, 0, (top + 1) | (3 << 62)]              # the two flag bits are cleared first, the rest is still >= r
+    accepted = [5, 6, 7, 8 | (1 << 63)]
+    st = Stream(rejected + accepted + [1, 2, 3, 4])
+    v = fr_rand(st)
+    assert v == (5 + (6 << 64) + (7 << 128) + (8 << 192)) * pow(R, -1, o.R_MOD) % o.R_MOD
+    assert len(st.words) == 4
+    import random
+    assert 0 <= fr_rand(random.Random(1)) < o.R_MOD
+
+
+# ------------------------------------------------------------------------------------------------ product-side verifier
+def test_product_verifiers_python_and_cpp(golden, test_zkey_bytes):
+    """Groth16.process_vk / verify_with_processed_vk / verify (src/zkey.rs:868-870, tests/groth16.rs:33-35) in both host
+    mirrors, on the golden proofs: accept, reject a wrong public input (tests/groth16.rs:42-74), reject a tampered proof,
+    MalformedVerifyingKey on an input-count mismatch; must agree with the oracle's independently built pairing."""
+    import subprocess
+    from circom_compat_b200 import Groth16, Proof, read_zkey, MalformedVerifyingKey, verifier
+    pk, cm = read_zkey(test_zkey_bytes)
+    z = o.read_zkey(test_zkey_bytes)
+    pvk = Groth16.process_vk(pk)
+    zk = os.path.join(ROOT, 'tests', 'golden', 'test.zkey')
+    for case in golden['test_zkey']['proofs']:
+        p = Proof(bytes.fromhex(case['proof_hex']))
+        assert Groth16.verify_with_processed_vk(pvk, [33], p) and o.verify(z, [33], (p.a, p.b, p.c))
+        assert not Groth16.verify_with_processed_vk(pvk, [34], p)
+        out = subprocess.check_output([HOST_BIN, '--verify', zk, case['proof_hex'], '33'], text=True) + \
+            subprocess.check_output([HOST_BIN, '--verify', zk, case['proof_hex'], '34'], text=True)
+        assert out.split() == ['verified=1', 'verified=0']
+    p = Proof(bytes.fromhex(golden['test_zkey']['proofs'][0]['proof_hex']))
+    assert Groth16.verify(pk, [33], p)
+    # tampered proofs: C replaced by A (on the curve, wrong), and a coordinate bit flip (off the curve)
+    swapped = Proof(p.data[:192] + p.data[:64])
+    assert not Groth16.verify_with_processed_vk(pvk, [33], swapped) and not o.verify(z, [33], (swapped.a, swapped.b, swapped.c))
+    flipped = bytearray(p.data); flipped[0] ^= 1
+    assert not Groth16.verify_with_processed_vk(pvk, [33], Proof(bytes(flipped)))
+    assert 'verified=0' in subprocess.check_output([HOST_BIN, '--verify', zk, swapped.data.hex(), '33'], text=True)
+    with pytest.raises(MalformedVerifyingKey):
+        Groth16.verify_with_processed_vk(pvk, [33, 1], p)
+    r = subprocess.run([HOST_BIN, '--verify', zk, p.data.hex()], capture_output=True, text=True)
+    assert r.returncode == 1 and 'MalformedVerifyingKey' in r.stderr
+    # pairing sanity on the product's tower arithmetic: bilinear, non-degenerate, order r
+    e = verifier.pairing(z.alpha_g1, z.beta_g2)
+    assert verifier.pairing(verifier.g1_mul(z.alpha_g1, 5), z.beta_g2) == verifier.f12_pow(e, 5)
+    assert e != verifier.F12_ONE and verifier.f12_pow(e, o.R_MOD) == verifier.F12_ONE
+
+
+def test_product_verifier_reference_bench_key(golden, complex_zkey_bytes):
+    # benches/groth16.rs:63-66: the proof of the 10 000-constraint chain verifies with inputs = full_assignment[1..num_inputs]
+    from circom_compat_b200 import Groth16, Proof, read_zkey
+    pk, cm = read_zkey(complex_zkey_bytes)
+    g = golden['complex_zkey']
+    w = o.chain_witness(pk.n_vars, g['a'])
+    p = Proof(bytes.fromhex(g['proof_hex']))
+    assert Groth16.verify(pk, w[1:cm.num_instance_variables], p)
+    assert not Groth16.verify(pk, [(w[1] + 1) % o.R_MOD], p)
+
+
 # ------------------------------------------------------------------------------------------------ output formats
 def test_proof_formats(golden, test_zkey_bytes):
     """Ethereum tuples (src/ethereum.rs) and ark-serialize encodings of a golden proof; the compressed form must
