@@ -11,6 +11,8 @@ Output: ONE JSON line (rank 0).  `value` = device-resident throughput (witness a
 Groth16.create_proof_with_reduction_and_matrices with a pinned HOST witness (H2D 32 B x n_vars and D2H 256 B inside the
 timed region), `roofline` = the dominant kernel (MSM bucket accumulation, G1) against measured HBM bandwidth,
 `cpu_baseline` = oracle/cref.c on the host cores, same key / witness / (r, s), proof bytes asserted identical.
+N > 1: the headline is N replicas (whole provers, weak scaling); `other_mode` is the same 2^20 proof base-sharded over the
+N GPUs (strong scaling: latency), and `config4` is BASELINE.json config 4: a 2^22 chain, MSM bases sharded over the N GPUs.
 """
 import argparse
 import json
@@ -122,6 +124,24 @@ def physical_cores():
     return max(1, (os.cpu_count() or 2) // 2)
 
 
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def pin_cpu_arm():
+    """One OpenMP thread per physical core, packed: without this the same 64-thread run moved 2.5x between boxes (threads
+    landing on SMT siblings / drifting across sockets).  Must be in the environment before libgomp is loaded (oracle/cref)."""
+    os.environ.setdefault('OMP_PLACES', 'cores')
+    os.environ.setdefault('OMP_PROC_BIND', 'close')
+    os.environ.setdefault('OMP_DYNAMIC', 'false')
+
+
 def cpu_setup(circ):
     """proving key from the CPU oracle only (reference arm: none of our kernels anywhere)"""
     from circom_compat_b200 import synth
@@ -135,10 +155,19 @@ def cpu_setup(circ):
     return synth.setup(CpuFixedBase(), circ)
 
 
+def workload_config(args, circ):
+    """names the WORKLOAD only - identical in both arms (how each arm runs it is reported beside it, not inside)"""
+    return {"workload": f"circom squaring chain (reference bench family, test-vectors/complex-circuit), domain 2^{args.log_n}, "
+                        f"n_vars={circ.n_vars}, constraints={circ.num_constraints}, BN254, synthetic trapdoor zkey seed 0xB200, fixed r,s",
+            "witness": args.workload, "log_n": args.log_n,
+            "l2": "inputs larger than L2 (proving-key tables ~6 GB per proof pass vs 126 MB L2)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    pin_cpu_arm()
     import numpy as np  # noqa: F401
     from oracle import cref
     from circom_compat_b200 import fr_to_mont
@@ -148,29 +177,37 @@ def run_reference(args):
     t0 = time.time()
     pk, _ = cpu_setup(circ)
     cm = circ.matrices()
-    log(f"[bench] CPU setup {time.time() - t0:.1f}s on {cores} threads")
+    log(f"[bench] CPU setup {time.time() - t0:.1f}s on {cores} threads ({cpu_model()}, nproc={os.cpu_count()})")
     za, wm = oracle_key(pk, cm), fr_to_mont(w)
     for _ in range(args.warmup):
         cref.prove(za, R_FIX, S_FIX, wm, nthreads=cores)
+    steps = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         cref.prove(za, R_FIX, S_FIX, wm, nthreads=cores)
+        steps.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
     val = args.steps / dt
-    sample = f"{args.steps} full proofs of the {args.workload} 2^{args.log_n} workload, oracle/cref.c (C + OpenMP restatement of ark-groth16 0.5), {cores} threads"
+    sample = f"{args.steps} full proofs of the {args.workload} 2^{args.log_n} workload, oracle/cref.c (C + OpenMP restatement of ark-groth16 0.5), {cores} threads pinned one per core"
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery)",
-           "data": "synthetic", "config": workload_config(args, circ),
-           "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample, "phases_s": cref.last_phase_seconds()},
+           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (254-bit Montgomery integers)",
+           "data": "synthetic", "config": workload_config(args, circ), "parallelism": f"{cores} OpenMP threads on the host",
+           "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port", "sample": sample, "phases_s": cref.last_phase_seconds(),
+                            "best_step_value": 1.0 / min(steps), "step_seconds": steps, "cpu_model": cpu_model(), "nproc": os.cpu_count(),
+                            "omp": {k: os.environ.get(k) for k in ('OMP_PLACES', 'OMP_PROC_BIND')}},
            "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(out)
 
 
-def workload_config(args, circ):
-    return {"workload": f"circom squaring chain (reference bench family, test-vectors/complex-circuit), domain 2^{args.log_n}, "
-                        f"n_vars={circ.n_vars}, constraints={circ.num_constraints}, BN254, synthetic trapdoor zkey seed 0xB200, fixed r,s",
-            "witness": args.workload, "log_n": args.log_n, "parallelism": None,
-            "l2": "inputs larger than L2 (proving-key tables ~6 GB per proof pass vs 126 MB L2)"}
+def static_kernel_profile():
+    """per-launch DRAM traffic and IMAD.WIDE count of the dominant kernel come from an ncu capture, not from this run: the
+    committed summary profiles/kernel_profile.json (written by tools/ncu_summary.py from the capture named inside it)."""
+    p = os.path.join(ROOT, 'profiles', 'kernel_profile.json')
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -184,23 +221,10 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         import datetime
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=120))
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=300))
     from circom_compat_b200 import Context, Groth16, CircomReduction, fr_to_mont, fr_from_mont, synth, sharding, release_all
+    from circom_compat_b200.zkey import Q_MOD
     dev = f'cuda:{local}'
-    inflight = max(1, args.inflight)
-
-    circ, w = build_workload(args.log_n, args.workload)
-    setup_ctx = Context(local)
-    t0 = time.time()
-    pk, td = synth.setup(setup_ctx, circ)
-    cm = circ.matrices()
-    log(f"[bench] rank {rank}: trapdoor setup + GPU fixed-base key generation {time.time() - t0:.1f}s")
-    wm_np = fr_to_mont(w)
-    pinned = [torch.empty(wm_np.shape, dtype=torch.int64).pin_memory() for _ in range(inflight)]
-    wms = [p_.numpy().view(np.uint64) for p_ in pinned]
-    for w_ in wms:
-        w_[...] = wm_np
-    n_vars = circ.n_vars
 
     def barrier():
         torch.cuda.synchronize()
@@ -218,14 +242,44 @@ def run_ours(args):
         ths = [threading.Thread(target=fn, args=(i,)) for i in range(n)]
         [t_.start() for t_ in ths]; [t_.join() for t_ in ths]
 
-    def measure(mode):
-        """mode: 'single' / 'replicas' (whole proofs per GPU) or 'sharded' (MSM base ranges over the GPUs, NCCL all-gather)."""
+    setup_ctx = Context(local)
+
+    class Workload:
+        def __init__(self, log_n, kind, inflight):
+            self.log_n = log_n
+            self.circ, self.w = build_workload(log_n, kind)
+            t0 = time.time()
+            self.pk, self.td = synth.setup(setup_ctx, self.circ)
+            self.cm = self.circ.matrices()
+            log(f"[bench] rank {rank}: 2^{log_n} trapdoor setup + GPU fixed-base key generation {time.time() - t0:.1f}s")
+            self.wm_np = fr_to_mont(self.w)
+            self.pinned = [torch.empty(self.wm_np.shape, dtype=torch.int64).pin_memory() for _ in range(inflight)]
+            self.wms = [p_.numpy().view(np.uint64) for p_ in self.pinned]
+            for w_ in self.wms:
+                w_[...] = self.wm_np
+
+        def check_closed_form(self, proof):
+            """the unique proof under the trapdoor, from a closed form that uses no h (synth.expected_proof_dlogs_independent):
+            H term = (a(tau) b(tau) - c(tau)) / delta, so it checks the witness map, the five MSMs and the assembly"""
+            da, db, dc = synth.expected_proof_dlogs_independent(self.td, self.circ, self.w, R_FIX, S_FIX)
+            ea = setup_ctx.fixed_base_g1(synth._ints_to_limbs([da, dc])); eb = setup_ctx.fixed_base_g2(synth._ints_to_limbs([db]))
+            qinv = pow(1 << 256, -1, Q_MOD)
+            def canon(a): return [int.from_bytes(np.ascontiguousarray(a).tobytes()[i:i + 32], 'little') * qinv % Q_MOD for i in range(0, a.size * 8, 32)]
+            exp = canon(ea[0]) + canon(eb[0]) + canon(ea[1])
+            got = [int.from_bytes(proof.data[i:i + 32], 'little') for i in range(0, 256, 32)]
+            assert exp == got, "proof does not match the trapdoor's closed-form expectation"
+            # second, h-based form: additionally pins h . h_query == (ab - c)(tau) / delta for the GPU's own h
+            h = fr_from_mont(CircomReduction.witness_map_from_matrices(self.cm, self.circ.num_inputs, self.circ.num_constraints, self.wms[0], setup_ctx))
+            assert synth.expected_proof_dlogs(self.td, self.w, h, R_FIX, S_FIX, self.circ.num_inputs) == (da, db, dc), "witness map disagrees with the trapdoor"
+
+    def measure(wl, mode, steps, warmup, want_inflight):
+        """mode: 'single' / 'replicas' (whole proofs per GPU) or 'sharded' (MSM base ranges over the GPUs, partials exchanged
+        through NVLink peer memory inside the captured proof graph, or with one NCCL all-gather)."""
         sharded = mode == 'sharded'
-        # sharded proofs are issued one at a time: two host threads issuing collectives of two communicators onto the
-        # same CUDA stream in rank-dependent order can deadlock (seen with 2 in flight); latency is what sharding buys
-        inflight = 1 if sharded else max(1, args.inflight)
+        pk, cm, circ = wl.pk, wl.cm, wl.circ
+        # a sharded proof occupies every GPU for its whole duration; what sharding buys is latency, so one is in flight
+        inflight = 1 if sharded else max(1, want_inflight)
         ctxs = [Context(local, rank if sharded else 0, world if sharded else 1) for _ in range(inflight)]
-        groups = [None] * inflight
         fused = sharded and args.exchange == 'p2p'
         if fused:
             sharding.connect_p2p(ctxs[0], dist)                    # CUDA-IPC handles of the exchange buffers, once
@@ -234,10 +288,10 @@ def run_ours(args):
 
         def one_proof(i=0):
             if not sharded:
-                return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wms[i], ctxs[i])
+                return Groth16.create_proof_with_reduction_and_matrices(pk, R_FIX, S_FIX, cm, circ.num_inputs, circ.num_constraints, wl.wms[i], ctxs[i])
             if fused:
-                return Groth16.prove_sharded_p2p(pk, cm, R_FIX, S_FIX, wms[i], ctxs[i])
-            return sharding.prove_sharded(ctxs[i], pk, cm, wms[i], R_FIX, S_FIX, dist, dev, groups[i])
+                return Groth16.prove_sharded_p2p(pk, cm, R_FIX, S_FIX, wl.wms[i], ctxs[i])
+            return sharding.prove_sharded(ctxs[i], pk, cm, wl.wms[i], R_FIX, S_FIX, dist, dev, None)
 
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max_workers=inflight)          # persistent host threads: one per in-flight proof
@@ -253,33 +307,32 @@ def run_ours(args):
 
         t0 = time.time()
         proofs = [one_proof(i) for i in range(inflight)]                 # loads the key (tables) on first use
-        log(f"[bench] rank {rank} {mode}: key load + first proofs {time.time() - t0:.1f}s")
+        log(f"[bench] rank {rank} {mode} 2^{wl.log_n}: key load + first proofs {time.time() - t0:.1f}s")
         assert all(p_.data == proofs[0].data for p_ in proofs)
-        run_steps(max(args.warmup, inflight))
+        run_steps(max(warmup, inflight))
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         launches0 = ctxs[0].launch_count()
         t0 = time.perf_counter()
-        proof = run_steps(args.steps)                                     # e2e: host witness in, proof bytes out, every step
+        proof = run_steps(steps)                                          # e2e: host witness in, proof bytes out, every step
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         launches = ctxs[0].launch_count() - launches0
-        timings = ctxs[0].last_timings()
-        res = {"mode": mode, "proof": proof, "launches": launches, "timings": timings, "e2e_s": e2e_s, "ctxs": ctxs}
+        res = {"mode": mode, "proof": proof, "launches": launches, "e2e_s": e2e_s, "ctxs": ctxs, "inflight": inflight}
         per_step = world if mode == 'replicas' else 1                    # replicas: every rank proves its own copy
-        res["e2e_value"] = per_step * args.steps / e2e_s
+        res["e2e_value"] = per_step * steps / e2e_s
         if not sharded:
             # device-resident: witness already in HBM, CUDA events inside the library, same number in flight
             barrier()
-            per = [args.steps // inflight + (1 if i < args.steps % inflight else 0) for i in range(inflight)]
+            per = [steps // inflight + (1 if i < steps % inflight else 0) for i in range(inflight)]
             tot = [0.0] * inflight
             def dev_worker(i):
                 if per[i]:
                     tot[i] = ctxs[i].bench_device(pk, cm, per[i]) * per[i]
             threads(dev_worker, inflight)
-            dev_ms = max_over_ranks(max(tot) / args.steps)
+            dev_ms = max_over_ranks(max(tot) / steps)
             barrier()
             res["value"] = per_step * 1e3 / dev_ms
             res["latency_ms"] = ctxs[0].bench_device(pk, cm, 5)
@@ -295,101 +348,134 @@ def run_ours(args):
         pool.shutdown()
         return res
 
+    def phase_table(wl, sharded):
+        """per-phase CUDA-event times of one proof issued WITHOUT the captured graph (the graph has no interior events)"""
+        os.environ['B2G_GRAPH'] = '0'
+        try:
+            cx = Context(local, rank if sharded else 0, world if sharded else 1)
+        finally:
+            os.environ.pop('B2G_GRAPH', None)
+        if sharded:
+            Groth16.prove_partial(wl.pk, wl.cm, wl.wms[0], cx, R_FIX, S_FIX)
+            Groth16.prove_partial(wl.pk, wl.cm, wl.wms[0], cx, R_FIX, S_FIX)
+        else:
+            for _ in range(2):
+                Groth16.create_proof_with_reduction_and_matrices(wl.pk, R_FIX, S_FIX, wl.cm, wl.circ.num_inputs, wl.circ.num_constraints, wl.wms[0], cx)
+        t = cx.last_timings()
+        cx.close()
+        return t
+
+    inflight = max(1, args.inflight)
+    wl = Workload(args.log_n, args.workload, inflight)
     main_mode = 'single' if world == 1 else args.mode
-    main = measure(main_mode)
+    main = measure(wl, main_mode, args.steps, args.warmup, inflight)
     proof = main["proof"]
     ctx = main["ctxs"][0]
 
-    # correctness gate: closed-form discrete logs of the unique proof under the trapdoor
     if rank == 0 and not args.skip_check:
-        from circom_compat_b200.zkey import Q_MOD
-        h = fr_from_mont(CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wms[0], setup_ctx))
-        da, db, dc = synth.expected_proof_dlogs(td, w, h, R_FIX, S_FIX, circ.num_inputs)
-        ea = setup_ctx.fixed_base_g1(synth._ints_to_limbs([da, dc])); eb = setup_ctx.fixed_base_g2(synth._ints_to_limbs([db]))
-        qinv = pow(1 << 256, -1, Q_MOD)
-        def canon(a): return [int.from_bytes(np.ascontiguousarray(a).tobytes()[i:i + 32], 'little') * qinv % Q_MOD for i in range(0, a.size * 8, 32)]
-        exp = canon(ea[0]) + canon(eb[0]) + canon(ea[1])
-        got = [int.from_bytes(proof.data[i:i + 32], 'little') for i in range(0, 256, 32)]
-        assert exp == got, "proof does not match the trapdoor's closed-form expectation"
-        log("[bench] proof matches the trapdoor closed form")
+        wl.check_closed_form(proof)
+        log("[bench] proof matches the trapdoor closed form (h-independent) and the witness map matches the trapdoor")
 
     roof, extra = None, {}
     if rank == 0:
         peak, how = measured_peaks()
         shard_div = world if main_mode == 'sharded' else 1
-        # dominant kernel: msm_accumulate_kernel<G1> on the H query (n = domain bases / scalars), run alone
+        pk, cm = wl.pk, wl.cm
+        # dominant kernel group: the bucket accumulation of one G1 MSM (H query: n = domain bases / scalars), run alone
         msm_ms, acc_ms = ctx.bench_msm(pk, cm, 0, 5)
         alg = pk.domain_size // shard_div * 96.0
-        roof = {"bound": "hbm", "kernel": "msm_accumulate_kernel<G1> (H query)", "achieved": alg / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": 2.076e9 / shard_div, "peak_source": how, "algorithmic_bytes": alg,
-                "kernel_ms": acc_ms, "whole_msm_ms": msm_ms,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^20 (profiles/r1_ncu_summary_final.txt, kernel id 11)",
-                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, 85.4 % busy in ncu, not by HBM (DESIGN.md section 5)"}
-        # the binding roofline: IMAD.WIDE issue slots (fmaheavy pipe).  Slots per mixed add are a static property of the
-        # kernel (ncu: 85.4 % of 4.66 M cycles/SMSP busy over 15 x 2^20 adds -> 1198 IMAD.WIDE-equivalents per G1 add);
-        # adds per launch = non-zero digits (here all n * windows, windows = ceil(255 / c) with the library's window rule);
-        # peak = 148 SMs x 4 SMSPs x 32 lanes / 4 cycles x 1.965 GHz.
-        n_h = pk.domain_size // shard_div
-        if args.log_n >= 19 and not os.environ.get('B2G_MSM_C'):
-            c_win = 17 if n_h >= (3 << 18) else 16                  # msm_pick_c (csrc/msm.cuh)
-            nwin = -(-255 // c_win)
-            adds = n_h * nwin
-            peak_int = 148 * 4 * 32 / 4 * 1.965e9
-            ach_int = adds * 1198.0 / (acc_ms * 1e-3)
+        prof = static_kernel_profile() or {}
+        roof = {"bound": "hbm", "kernel": "G1 bucket accumulation (H query): " + prof.get("g1_kernels", "msm_accumulate_kernel<G1>"),
+                "achieved": alg / (acc_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg / (acc_ms * 1e-3) / 1e9 / peak, "traffic": (prof.get("g1_dram_bytes_per_launch") or 0) / shard_div or None, "peak_source": how,
+                "algorithmic_bytes": alg, "kernel_ms": acc_ms, "whole_msm_ms": msm_ms,
+                "traffic_source": "static: " + prof.get("source", "no committed ncu summary (profiles/kernel_profile.json missing)"),
+                "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, not by HBM (DESIGN.md section 5)"}
+        if prof.get("g1_imad_wide_per_launch") and args.log_n == prof.get("log_n") and shard_div == 1:
+            peak_int = 148 * 4 * 32 / 4 * 1.965e9           # 148 SMs x 4 sub-partitions x 32 lanes, one IMAD.WIDE per 4 cycles, 1.965 GHz
+            ach_int = prof["g1_imad_wide_per_launch"] / (acc_ms * 1e-3)
             roof["int_pipe"] = {"bound": "IMAD.WIDE issue (fmaheavy pipe)", "achieved": ach_int / 1e12, "peak": peak_int / 1e12, "unit": "T IMAD.WIDE/s",
-                                "frac": ach_int / peak_int, "mixed_adds_per_launch": adds, "windows": nwin, "window_bits": c_win, "imad_wide_per_add": 1198,
-                                "source": "adds x IMAD.WIDE-equivalents per add / live CUDA-event kernel time; count and peak rate from profiles/r1_ncu_summary_final.txt"}
+                                "frac": ach_int / peak_int, "imad_wide_per_launch": prof["g1_imad_wide_per_launch"],
+                                "source": "static thread-level IMAD.WIDE count of the kernel group (" + prof.get("source", "") + ") / live CUDA-event time"}
         g2_ms, g2_acc = ctx.bench_msm(pk, cm, 4, 3)
         extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / shard_div * 160.0 / (g2_acc * 1e-3) / 1e9}
-        extra["phase_ms_last_proof"] = main["timings"]
-        extra["in_flight"] = len(main["ctxs"])
         extra["single_proof_latency_ms"] = main["latency_ms"]
     for c_ in main["ctxs"]:
         c_.close()
+    if rank == 0:
+        extra["phase_ms_one_proof_alone"] = phase_table(wl, main_mode == 'sharded')
 
     other = None
     if world > 1 and not args.one_mode:
         other_mode = 'sharded' if main_mode == 'replicas' else 'replicas'
-        o_ = measure(other_mode)
+        o_ = measure(wl, other_mode, args.steps, args.warmup, inflight)
         assert o_["proof"].data == proof.data, "sharded and whole proofs differ"
         other = {"mode": other_mode, "value": o_["value"], "e2e_value": o_["e2e_value"], "unit": "proofs/s", "latency_ms": o_["latency_ms"],
-                 "scaling": "strong" if other_mode == 'sharded' else "weak", "gpu_launches": o_["launches"],
+                 "scaling": "strong" if other_mode == 'sharded' else "weak", "gpu_launches": o_["launches"], "in_flight": o_["inflight"],
                  "exchange": args.exchange if other_mode == 'sharded' else None}
         for c_ in o_["ctxs"]:
             c_.close()
+        if rank == 0 and other_mode == 'sharded':
+            other["phase_ms_one_proof_alone"] = phase_table(wl, True)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:     # the CPU leg is reported at N = 1 only
+        pin_cpu_arm()
         from oracle import cref
         cref.build()
         cores = physical_cores()
-        za = oracle_key(pk, cm)
+        za = oracle_key(wl.pk, wl.cm)
         t0 = time.perf_counter()
-        ref = cref.prove(za, R_FIX, S_FIX, wm_np, nthreads=cores)
+        ref = cref.prove(za, R_FIX, S_FIX, wl.wm_np, nthreads=cores)
         dt = time.perf_counter() - t0
         assert ref == proof.data, "GPU proof bytes differ from the CPU oracle's"
         log(f"[bench] CPU oracle proof identical to the GPU proof; {dt:.2f}s on {cores} threads")
         cpu = {"value": 1.0 / dt, "unit": "proofs/s", "cores": cores, "kind": "port",
-               "sample": "1 full proof of the same workload (same key, witness, r, s), oracle/cref.c C+OpenMP restatement of the ark-groth16 0.5 CPU path; proof bytes asserted identical",
-               "phases_s": cref.last_phase_seconds()}
+               "sample": "1 full proof of the same workload (same key, witness, r, s), oracle/cref.c C+OpenMP restatement of the ark-groth16 0.5 CPU path, one pinned thread per core; proof bytes asserted identical",
+               "phases_s": cref.last_phase_seconds(), "cpu_model": cpu_model(), "nproc": os.cpu_count()}
+
+    cfg = workload_config(args, wl.circ)
+    n_vars = wl.circ.n_vars
+
+    # BASELINE.json config 4: 2^22-constraint chain, MSM bases sharded by range over the N GPUs
+    config4 = None
+    if world > 1 and not args.no_config4:
+        release_all()
+        del wl
+        wl4 = Workload(22, 'chain', 1)
+        m4 = measure(wl4, 'sharded', args.steps4, 2, 1)
+        if rank == 0:
+            if not args.skip_check:
+                wl4.check_closed_form(m4["proof"])
+                log("[bench] 2^22 sharded proof matches the trapdoor closed form (h-independent)")
+            config4 = {"workload": "circom squaring chain, domain 2^22 (n_vars=4194304), MSM bases sharded by range over %d GPUs" % world,
+                       "value": m4["value"], "unit": "proofs/s", "latency_ms": m4["latency_ms"], "steps": args.steps4, "in_flight": 1,
+                       "exchange": args.exchange, "gpu_launches": m4["launches"], "scaling": "strong",
+                       "checked": None if args.skip_check else "proof == trapdoor closed form (no h involved)"}
+        for c_ in m4["ctxs"]:
+            c_.close()
+        if rank == 0:
+            config4["phase_ms_one_proof_alone"] = phase_table(wl4, True)
 
     if rank == 0:
-        cfg = workload_config(args, circ)
-        cfg["in_flight"] = 1 if main_mode == "sharded" else inflight
-        cfg["parallelism"] = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs; 768 B partials exchanged " + ("inside the assembly kernels over NVLink peer memory" if args.exchange == 'p2p' else "with one NCCL all-gather")
-                                                              if main_mode == 'sharded' else f"{world} replicas (one whole prover per GPU)")
         sharded = main_mode == 'sharded'
         value = main["value"]
         per_step = world if main_mode == 'replicas' else 1
+        parallelism = "single GPU" if world == 1 else (f"MSM base-range sharding over {world} GPUs; 768 B partials exchanged " + ("inside the proof graph over NVLink peer memory" if args.exchange == 'p2p' else "with one NCCL all-gather")
+                                                       if sharded else f"{world} replicas (one whole prover per GPU)")
         out = {"metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1e3 / value * per_step, "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak", "vs_baseline": None,
-               "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic", "config": cfg, "clocks": main["clocks"],
-               "e2e": {"value": main["e2e_value"], "unit": "proofs/s", "h2d_bytes_per_step": n_vars * 32 + (768 * world if sharded else 0),
-                       "d2h_bytes_per_step": 256 + (768 * (world + 1) if sharded else 0), "ms_per_step": 1e3 * main["e2e_s"] / args.steps},
+               "ms_per_step": 1e3 / value * per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+               "dtype": "u32x8 (254-bit Montgomery integers)", "data": "synthetic", "config": cfg, "parallelism": parallelism, "in_flight": main["inflight"],
+               "clocks": main["clocks"],
+               "e2e": {"value": main["e2e_value"], "unit": "proofs/s", "h2d_bytes_per_step": n_vars * 32 + 64 + (768 * world if sharded and args.exchange != 'p2p' else 0),
+                       "d2h_bytes_per_step": 256 + (768 * (world + 1) if sharded and args.exchange != 'p2p' else 0), "ms_per_step": 1e3 * main["e2e_s"] / args.steps,
+                       "host_driver": f"{main['inflight']} host threads, one Context each; one captured CUDA graph launch per proof"},
                "gpu_launches": main["launches"], "roofline": roof, "cpu_baseline": cpu}
         out.update(extra)
         if other:
             out["other_mode"] = other
+        if config4:
+            out["config4"] = config4
         emit(out)
     release_all()
     setup_ctx.close()
@@ -421,6 +507,8 @@ def main():
     ap.add_argument('--mode', default='replicas', choices=['sharded', 'replicas'], help='N>1: headline mode (the other one is measured too, see other_mode)')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded mode: partials folded from NVLink peer memory inside the kernels (p2p) or gathered with one NCCL all-gather (nccl)')
     ap.add_argument('--one-mode', action='store_true', help='N>1: measure only --mode')
+    ap.add_argument('--no-config4', action='store_true', help='N>1: skip the 2^22 base-sharded leg (BASELINE.json config 4)')
+    ap.add_argument('--steps4', type=int, default=5, help='timed proofs of the 2^22 leg')
     ap.add_argument('--inflight', type=int, default=3, help='proofs in flight per GPU (one Context + host thread each)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--skip-check', action='store_true')

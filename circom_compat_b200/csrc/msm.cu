@@ -550,12 +550,12 @@ void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, b
     CUDA_CHECK(cudaMalloc(&s.buckets, (size_t)nbuckets * pt));
     CUDA_CHECK(cudaMalloc(&s.partials, (npart + 1) * pt));
     CUDA_CHECK(cudaMalloc(&s.result, pt)); s.result_owned = true;
-    // batched-affine pre-reduction (4a): R levels when the average bucket holds enough points to halve R times and still
-    // leave the XYZZ stage ~16-32 per bucket; small problems (latency-bound) skip it.  B2G_MSM_AFFINE_ROUNDS overrides.
+    // batched-affine pre-reduction (4a): OFF by default.  Measured on B200 at 2^20 x 15 windows (profiles/r2_affine_rounds.md):
+    // the 36 % multiply saving is eaten by the DRAM traffic of the three-pass structure (every 64-byte gather costs 128 B of
+    // DRAM, twice per level, plus the intermediate lists) and by the latency of the shared inversion; R = 1..4 levels were
+    // 20-50 % slower than the XYZZ kernel alone and throughput-neutral inside a whole proof.  B2G_MSM_AFFINE_ROUNDS=R opts in.
     {
-        const uint64_t avg = nent / (nbuckets ? nbuckets : 1);
         int rounds = 0;
-        if (nent >= (1ull << 21)) { uint64_t a = avg; while (a >= 48 && rounds < MSM_AFF_MAX_ROUNDS) { a >>= 1; rounds++; } }
         const char* ov = getenv("B2G_MSM_AFFINE_ROUNDS");
         if (ov && *ov) { long x = strtol(ov, nullptr, 10); rounds = x < 0 ? 0 : (x > MSM_AFF_MAX_ROUNDS ? MSM_AFF_MAX_ROUNDS : (int)x); }
         s.aff_cap_rounds = rounds;

@@ -37,35 +37,48 @@ using namespace b2g;
 struct b2g_ctx {
     int device = 0, shard_rank = 0, shard_count = 1;
     cudaStream_t st[NQ] = {}, st_glue = nullptr;
-    cudaEvent_t ev_w = nullptr, ev_sort = nullptr, ev_pre = nullptr, ev_post = nullptr, ev_done[NQ] = {}, ev_t[20] = {};
+    cudaEvent_t ev_w = nullptr, ev_sort = nullptr, ev_pre = nullptr, ev_fork = nullptr, ev_done[NQ] = {}, ev_t[20] = {};
     MsmScratch scratch[NQ];
     bool scratch_ok = false;
-    uint8_t* d_partial = nullptr;        // 768 B: [H, L, A, B1] G1 XYZZ + B2 G2 XYZZ
-    uint8_t* d_partials_all = nullptr;   // up to 64 ranks
+    uint8_t* d_partial = nullptr;        // REC_BYTES: the public partial [H, L, A, B1] G1 XYZZ + B2 G2 XYZZ (768 B), then [s*A, r*B1]
+    uint8_t* d_partials_all = nullptr;   // up to 64 ranks x REC_BYTES
     uint8_t* d_proof = nullptr;          // 256 B
-    uint8_t* d_pre = nullptr;            // glue precomputation: r*d1, s*d1, rs*d1 (G1 XYZZ) + s*d2 (G2 XYZZ)
+    uint8_t* d_pre = nullptr;            // glue precomputation: r*d1, s*d1, rs*d1, K_C (G1 XYZZ) + s*d2 (G2 XYZZ)
     fe *d_w = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
     size_t cap_w = 0, cap_n = 0;
     float last_ms[16] = {};
     bool pre_valid = false; uint32_t pre_r[8] = {}, pre_s[8] = {};   // (r, s) whose glue_pre result sits in d_pre
+    uint8_t *d_rs = nullptr, *h_rs = nullptr;  // r | s (canonical, 2 x 32 B): device copy read by the glue kernels, pinned staging
+    // One proof's whole device pipeline (all streams, ~100 launches) captured once per (key, matrices) as a CUDA graph and
+    // replayed with a single launch: the host cost of a proof drops from ~130 driver calls to a handful (B2G_GRAPH=0 disables)
+    bool use_graph = true;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};             // [0] whole proof, [1] sharded proof with the peer-memory exchange
+    uint64_t g_key[2][3] = {};                                  // (key uid, matrices uid, buffer generation) each graph was captured for
+    uint64_t alloc_gen = 1;                                    // bumped whenever a buffer the graphs point into is (re)allocated
+    uint64_t g_launches[2] = {0, 0};
+    unsigned long long* d_epoch = nullptr;                     // exchange epoch (device-resident so that it survives graph replay)
     // peer-memory exchange (b2g_prove_sharded_p2p): own buffer + every rank's buffer as seen from this device
     uint8_t* d_xchg = nullptr;                 // XCHG_BYTES: 2 slots x {epoch u64 @0, partial @256}
     uint8_t** d_peer_ptrs = nullptr;           // device array [shard_count]
     void* peer_mapped[64] = {};                // cudaIpcOpenMemHandle results (to close)
     int peers_imported = 0;
-    unsigned long long epoch = 0;
 };
 
+static std::atomic<uint64_t> g_next_uid{1};            // handles are told apart by uid, not by address (addresses get reused)
+
 struct b2g_pk {
+    uint64_t uid = g_next_uid++;
     int device = 0, shard_rank = 0, shard_count = 1;   // a key may be used by any ctx of the same device and shard
     uint32_t n_vars = 0, n_public = 0, domain = 0;
     MsmPlan plan[NQ];
     uint32_t lo[NQ] = {}, cnt[NQ] = {}, scalar_off[NQ] = {};
     uint8_t* d_consts = nullptr;         // G1: alpha, beta, delta, a_query[0], b_g1_query[0] (5 x 64) ; G2: beta, delta, b_g2_query[0] (3 x 128)
     void *d_tab_delta1 = nullptr, *d_tab_delta2 = nullptr;   // 8-bit window tables of delta_g1 / delta_g2 (32 x 255 affine points)
+    void *d_tab_aa = nullptr, *d_tab_bb = nullptr;           // same for alpha_g1 + a_query[0] and beta_g1 + b_g1_query[0] (glue_pre: K_C)
 };
 
 struct b2g_mat {
+    uint64_t uid = g_next_uid++;
     int device = 0;
     uint32_t m = 0, num_inputs = 0, n_vars = 0, n = 0;
     int logn = 0;
@@ -106,58 +119,106 @@ __device__ __forceinline__ typename C::Pt warp_fixed_mul(const void* __restrict_
     }
     return sh[0];
 }
-// pre[0] = r*delta1, pre[1] = s*delta1, pre[2] = (r*s)*delta1 (G1 XYZZ, 128 B each); then s*delta2 (G2 XYZZ, 256 B).
-// delta is fixed per key: its 8-bit window tables are built at b2g_pk_load, so each product is 32 table look-ups and a
-// 5-level tree inside one warp instead of a 254-step double-and-add on one thread (which bounded small-circuit latency).
-__global__ void __launch_bounds__(128) glue_pre_kernel(const void* __restrict__ tab_d1, const void* __restrict__ tab_d2, Scalar256 r, Scalar256 s,
-                                                       uint8_t* __restrict__ pre) {
-    __shared__ G1::Pt sh1[3][32];
+// pre[0] = r*delta1, pre[1] = s*delta1, pre[2] = (r*s)*delta1, pre[3] = K_C = s*(alpha1 + a_query[0]) + r*(beta1 + b_g1_query[0])
+// + (r*s)*delta1 (G1 XYZZ, 128 B each); then s*delta2 (G2 XYZZ, 256 B).  Every base here is fixed per key: its 8-bit window
+// table is built at b2g_pk_load, so each product is 32 table look-ups and a 5-level tree inside one warp instead of a
+// 254-step double-and-add on one thread.  K_C is what is left of C = s*A + r*B1 - rs*delta1 + L + H once the MSM results
+// are taken out:  C = K_C + s*msm_A + r*msm_B1 + msm_L + msm_H  (A = alpha + a0 + msm_A + r*delta1, B1 likewise).
+constexpr size_t PRE_BYTES = 4 * 128 + 256;
+__global__ void __launch_bounds__(192) glue_pre_kernel(const void* __restrict__ tab_d1, const void* __restrict__ tab_d2, const void* __restrict__ tab_aa,
+                                                       const void* __restrict__ tab_bb, const Scalar256* __restrict__ rs, uint8_t* __restrict__ pre) {
+    __shared__ G1::Pt sh1[5][32];
     __shared__ G2::Pt sh2[32];
+    __shared__ G1::Pt res[5];
+    const Scalar256 r = rs[0], s = rs[1];
     const int warp = threadIdx.x >> 5;
-    if (warp < 3) {
-        Scalar256 k = (warp == 0) ? r : s;
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (warp < 5) {
+        // warp 0: r*d1   1: s*d1   2: rs*d1   3: s*(alpha + a0)   4: r*(beta1 + b0)
+        Scalar256 k = (warp == 0 || warp == 4) ? r : s;
         if (warp == 2) {
             fe rc, sc;                                   // Scalar256 is only 4-byte aligned: copy limb by limb
             #pragma unroll
             for (int i = 0; i < 8; i++) { rc.l[i] = r.l[i]; sc.l[i] = s.l[i]; }
             fe rm = Fr::from_canonical(rc), sm = Fr::from_canonical(sc);
-            fe rs = Fr::to_canonical(Fr::mul(rm, sm));
+            fe rs_ = Fr::to_canonical(Fr::mul(rm, sm));
             #pragma unroll
-            for (int i = 0; i < 8; i++) k.l[i] = rs.l[i];
+            for (int i = 0; i < 8; i++) k.l[i] = rs_.l[i];
         }
-        G1::Pt p = warp_fixed_mul<G1, Fq>(tab_d1, k.l, sh1[warp]);
-        if ((threadIdx.x & 31) == 0) pt_store<Fq>(pre, warp, p);
+        const void* tab = warp < 3 ? tab_d1 : (warp == 3 ? tab_aa : tab_bb);
+        G1::Pt p = warp_fixed_mul<G1, Fq>(tab, k.l, sh1[warp]);
+        if (lead) { res[warp] = p; if (warp < 3) pt_store<Fq>(pre, warp, p); }
     } else {
         G2::Pt p = warp_fixed_mul<G2, Fq2>(tab_d2, s.l, sh2);
-        if ((threadIdx.x & 31) == 0) pt_store<Fq2>(pre + 3 * 128, 0, p);
+        if (lead) pt_store<Fq2>(pre + 4 * 128, 0, p);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        G1::Pt kc = res[2];
+        G1::add(kc, res[3]);
+        G1::add(kc, res[4]);
+        pt_store<Fq>(pre, 3, kc);
+    }
+}
+
+// out = k * p for one XYZZ point (the partial A / B1 MSM result of this rank) - issued on that MSM's own stream as soon as
+// it finishes, so the two variable-base scalar multiplications of the proof overlap the longest MSM instead of following it
+__global__ void scale_partial_kernel(const uint8_t* __restrict__ pt, const Scalar256* __restrict__ k, uint8_t* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    const Scalar256 kk = *k;
+    G1::Pt p = pt_load<Fq>(pt, 0);
+    pt_store<Fq>(out, 0, G1::mul_scalar(p, kk.l));       // k == 0 -> infinity (r == 0: B1 drops out, prover.rs)
 }
 
 __device__ __forceinline__ void store_canon(uint8_t* out, int slot, const fe& v) { fe_store(out + 32 * slot, Fq::to_canonical(v)); }
 
-// partials = count x 768 B.  Folds them in rank order and assembles the proof (ark-groth16 0.5.0 create_proof_with_assignment).
-__global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count, const uint8_t* __restrict__ consts,
-                                 const uint8_t* __restrict__ pre, Scalar256 r, Scalar256 s, uint8_t* __restrict__ proof) {
+// partials = count records of `stride` bytes: the 768-byte partial [H, L, A, B1 (G1 XYZZ), B2 (G2 XYZZ)] and, when
+// scaled_off >= 0, [s*A_k, r*B1_k] (G1 XYZZ) at that offset.  Folds them in rank order and assembles the proof
+// (ark-groth16 0.5.0 create_proof_with_assignment).  With the scaled points present no scalar multiplication is left here:
+// A, B2 and C are three independent sums, converted to affine by three warps side by side.
+__global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count, int stride, int scaled_off, const uint8_t* __restrict__ consts,
+                                 const uint8_t* __restrict__ pre, const Scalar256* __restrict__ rs, uint8_t* __restrict__ proof) {
     __shared__ G1::Pt shA, shB1, shsA, shrB1;
+    const Scalar256 r = rs[0], s = rs[1];
     const int warp = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
-    if (lead && warp < 2) {
+    const bool legacy = scaled_off < 0;
+    if (lead && (warp == 0 || (warp == 1 && legacy))) {
         // A = r*delta1 + a_query[0] + msm_A + alpha1 ;  B1 = s*delta1 + b_g1_query[0] + msm_B1 + beta1
         G1::Pt acc = pt_load<Fq>(pre, warp);
         G1::madd(acc, aff_load<Fq>(consts, warp == 0 ? 3 : 4));
-        for (int k = 0; k < count; k++) { G1::Pt q = pt_load<Fq>(partials + (size_t)k * B2G_PARTIAL_BYTES + (warp == 0 ? 256 : 384), 0); G1::add(acc, q); }
+        for (int k = 0; k < count; k++) { G1::Pt q = pt_load<Fq>(partials + (size_t)k * stride + (warp == 0 ? 256 : 384), 0); G1::add(acc, q); }
         G1::madd(acc, aff_load<Fq>(consts, warp == 0 ? 0 : 1));
         if (warp == 0) shA = acc; else shB1 = acc;
+        if (warp == 0 && !legacy) {
+            G1::Aff a = G1::to_affine(acc);
+            store_canon(proof, 0, a.x); store_canon(proof, 1, a.y);
+        }
+    }
+    if (lead && warp == 1 && !legacy) {
+        // C = K_C + sum_k (s*A_k + r*B1_k + L_k + H_k)
+        G1::Pt acc = pt_load<Fq>(pre, 3);
+        for (int k = 0; k < count; k++) {
+            const uint8_t* rec = partials + (size_t)k * stride;
+            G1::Pt q = pt_load<Fq>(rec + scaled_off, 0); G1::add(acc, q);
+            q = pt_load<Fq>(rec + scaled_off + 128, 0); G1::add(acc, q);
+            q = pt_load<Fq>(rec + 128, 0); G1::add(acc, q);
+            q = pt_load<Fq>(rec, 0); G1::add(acc, q);
+        }
+        G1::Aff c = G1::to_affine(acc);
+        store_canon(proof, 6, c.x); store_canon(proof, 7, c.y);
     }
     if (lead && warp == 2) {
         // B2 = s*delta2 + b_g2_query[0] + msm_B2 + beta2
-        G2::Pt acc = pt_load<Fq2>(pre + 3 * 128, 0);
+        G2::Pt acc = pt_load<Fq2>(pre + 4 * 128, 0);
         G2::madd(acc, aff_load<Fq2>(consts + 5 * 64, 2));
-        for (int k = 0; k < count; k++) { G2::Pt q = pt_load<Fq2>(partials + (size_t)k * B2G_PARTIAL_BYTES + 512, 0); G2::add(acc, q); }
+        for (int k = 0; k < count; k++) { G2::Pt q = pt_load<Fq2>(partials + (size_t)k * stride + 512, 0); G2::add(acc, q); }
         G2::madd(acc, aff_load<Fq2>(consts + 5 * 64, 0));
         G2::Aff b = G2::to_affine(acc);
         store_canon(proof, 2, b.x.c0); store_canon(proof, 3, b.x.c1); store_canon(proof, 4, b.y.c0); store_canon(proof, 5, b.y.c1);
     }
+    if (!legacy) return;
+    // host-mediated exchange (b2g_prove_partial / b2g_prove_finish): r, s may only arrive now, the scalar multiplications are done here
     __syncthreads();
     if (lead && warp == 0) shsA = G1::mul_scalar(shA, s.l);
     if (lead && warp == 1) shrB1 = G1::mul_scalar(shB1, r.l);            // r == 0 -> infinity: B1 is skipped (prover.rs)
@@ -173,8 +234,8 @@ __global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count
         G1::Pt rsd = G1::neg(pt_load<Fq>(pre, 2));
         G1::add(acc, rsd);
         for (int k = 0; k < count; k++) {
-            G1::Pt l = pt_load<Fq>(partials + (size_t)k * B2G_PARTIAL_BYTES + 128, 0); G1::add(acc, l);
-            G1::Pt h = pt_load<Fq>(partials + (size_t)k * B2G_PARTIAL_BYTES, 0); G1::add(acc, h);
+            G1::Pt l = pt_load<Fq>(partials + (size_t)k * stride + 128, 0); G1::add(acc, l);
+            G1::Pt h = pt_load<Fq>(partials + (size_t)k * stride, 0); G1::add(acc, h);
         }
         G1::Aff c = G1::to_affine(acc);
         store_canon(proof, 6, c.x); store_canon(proof, 7, c.y);
@@ -182,7 +243,8 @@ __global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count
 }
 
 // ------------------------------------------------------------------------------------------------ peer-memory exchange
-constexpr size_t XCHG_SLOT = 1280;                    // epoch word at +0, 768-byte partial at +256, padded
+constexpr size_t REC_BYTES = B2G_PARTIAL_BYTES + 256;  // device-side record of one rank: the public 768-byte partial + [s*A_k, r*B1_k]
+constexpr size_t XCHG_SLOT = 256 + REC_BYTES;         // epoch word at +0, record at +256
 constexpr size_t XCHG_BYTES = 2 * XCHG_SLOT;
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -195,14 +257,15 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 }
 
 // copy this rank's partial into its exchange slot and release the epoch (visible to peers over NVLink)
-__global__ void xchg_publish_kernel(const uint8_t* __restrict__ partial, uint8_t* __restrict__ xchg, unsigned long long epoch) {
+__global__ void xchg_publish_kernel(const uint8_t* __restrict__ partial, uint8_t* __restrict__ xchg, unsigned long long* __restrict__ epoch_ctr) {
+    const unsigned long long epoch = *epoch_ctr + 1ull;          // every rank counts its sharded proofs the same way
     uint8_t* slot = xchg + (epoch & 1ull) * XCHG_SLOT;
     const uint4* src = reinterpret_cast<const uint4*>(partial);
     uint4* dst = reinterpret_cast<uint4*>(slot + 256);
-    if (threadIdx.x < B2G_PARTIAL_BYTES / 16) dst[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x < REC_BYTES / 16) dst[threadIdx.x] = src[threadIdx.x];
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long*>(slot), epoch);
+    if (threadIdx.x == 0) { *epoch_ctr = epoch; st_release_sys(reinterpret_cast<unsigned long long*>(slot), epoch); }
 }
 
 // wait until every rank has published `epoch`, then gather the partials from peer memory (rank order) into `gathered`
@@ -214,8 +277,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 // The wait is bounded (a peer that never publishes must not wedge the GPU): after timeout_ns the rank's slot of
 // `timed_out` is set and the host reports B2G_E_DEVICE.
-__global__ void xchg_gather_kernel(uint8_t* const* __restrict__ peers, int count, unsigned long long epoch, uint8_t* __restrict__ gathered,
+__global__ void xchg_gather_kernel(uint8_t* const* __restrict__ peers, int count, const unsigned long long* __restrict__ epoch_ctr, uint8_t* __restrict__ gathered,
                                    unsigned long long timeout_ns, unsigned int* __restrict__ timed_out) {
+    const unsigned long long epoch = *epoch_ctr;      // incremented by this rank's publish kernel just before
     const int k = blockIdx.x;                         // one CTA per rank
     const uint8_t* slot = peers[k] + (epoch & 1ull) * XCHG_SLOT;
     if (threadIdx.x == 0) {
@@ -227,11 +291,11 @@ __global__ void xchg_gather_kernel(uint8_t* const* __restrict__ peers, int count
         }
     }
     __syncthreads();
-    if (threadIdx.x < B2G_PARTIAL_BYTES / 16) {
+    if (threadIdx.x < REC_BYTES / 16) {
         const uint4* src = reinterpret_cast<const uint4*>(slot + 256);
         uint4 v;
         asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + threadIdx.x) : "memory");
-        reinterpret_cast<uint4*>(gathered + (size_t)k * B2G_PARTIAL_BYTES)[threadIdx.x] = v;
+        reinterpret_cast<uint4*>(gathered + (size_t)k * REC_BYTES)[threadIdx.x] = v;
     }
 }
 
@@ -259,6 +323,13 @@ __device__ __forceinline__ G2::Aff g2_generator() {
 template <class C> struct Gen;
 template <> struct Gen<G1> { static __device__ __forceinline__ G1::Aff get() { return g1_generator(); } };
 template <> struct Gen<G2> { static __device__ __forceinline__ G2::Aff get() { return g2_generator(); } };
+
+// out = pts[i] + pts[j] (G1 affine, 64-byte records), affine
+__global__ void affine_sum_kernel(const uint8_t* __restrict__ pts, int i, int j, uint8_t* __restrict__ out) {
+    G1::Pt acc = G1::from_affine(aff_load<Fq>(pts, (size_t)i));
+    G1::madd(acc, aff_load<Fq>(pts, (size_t)j));
+    aff_store<Fq>(out, 0, G1::to_affine(acc));
+}
 
 // table[w][d-1] = d * 256^w * G (affine), w < 32, d = 1..255
 // base = nullptr: the group generator; else the affine point at `base` (e.g. delta of a proving key)
@@ -359,11 +430,11 @@ static void ensure_witness_buffers(b2g_ctx* ctx, size_t n_vars, size_t n) {
     if (n_vars > ctx->cap_w) {
         if (ctx->d_w) cudaFree(ctx->d_w);
         CUDA_CHECK(cudaMalloc(&ctx->d_w, (n_vars + 1) * sizeof(fe)));
-        ctx->cap_w = n_vars;
+        ctx->cap_w = n_vars; ctx->alloc_gen++;
     }
     if (n > ctx->cap_n) {
         for (fe** p : {&ctx->d_a, &ctx->d_b, &ctx->d_c, &ctx->d_h}) { if (*p) cudaFree(*p); CUDA_CHECK(cudaMalloc(p, n * sizeof(fe))); }
-        ctx->cap_n = n;
+        ctx->cap_n = n; ctx->alloc_gen++;
     }
 }
 
@@ -384,7 +455,7 @@ static void ensure_scratch(b2g_ctx* ctx, const b2g_pk* pk) {
         ctx->scratch[q].result = ctx->d_partial + PARTIAL_OFF[q];
         ctx->scratch[q].result_owned = false;
     }
-    ctx->scratch_ok = true;
+    ctx->scratch_ok = true; ctx->alloc_gen++;
 }
 
 static void run_witness_map(b2g_ctx* ctx, b2g_mat* mat, cudaStream_t st) {
@@ -422,7 +493,8 @@ static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
 // The four witness-scalar queries (L, A, B1, B2) are defined over the same index range and share ONE digit sort.
 static const int WITNESS_ORDER[4] = {Q_B2, Q_A, Q_B1, Q_L};     // the G2 MSM is the longest: start it first
 
-static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
+// scale: also compute s*msm_A and r*msm_B1 (d_rs must hold r, s) on those MSMs' own streams, right behind them
+static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed, bool scale) {
     cudaStream_t s0 = ctx->st[0], ssort = ctx->st[Q_L];
     CUDA_CHECK(cudaEventRecord(ctx->ev_w, s0));
     CUDA_CHECK(cudaStreamWaitEvent(ssort, ctx->ev_w, 0));
@@ -432,6 +504,11 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed) {
         if (q != Q_L) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sort, 0));
         if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q], ctx->st[q]));
         msm_accumulate(pk->plan[q], ctx->scratch[Q_L], ctx->scratch[q], ctx->st[q]);
+        if (scale && (q == Q_A || q == Q_B1)) {
+            const Scalar256* rs = reinterpret_cast<const Scalar256*>(ctx->d_rs);
+            scale_partial_kernel<<<1, 32, 0, ctx->st[q]>>>(ctx->d_partial + PARTIAL_OFF[q], q == Q_A ? rs + 1 : rs, ctx->d_partial + B2G_PARTIAL_BYTES + (q == Q_A ? 0 : 128));
+            g_launch_count += 1;
+        }
         if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q + 1], ctx->st[q]));
         CUDA_CHECK(cudaEventRecord(ctx->ev_done[q], ctx->st[q]));
     }
@@ -450,28 +527,96 @@ static void pk_release(b2g_pk* pk) {
     if (pk->d_consts) cudaFree(pk->d_consts);
     if (pk->d_tab_delta1) cudaFree(pk->d_tab_delta1);
     if (pk->d_tab_delta2) cudaFree(pk->d_tab_delta2);
+    if (pk->d_tab_aa) cudaFree(pk->d_tab_aa);
+    if (pk->d_tab_bb) cudaFree(pk->d_tab_bb);
     delete pk;
 }
 
-static Scalar256 load_scalar(const void* p) { Scalar256 s; memcpy(s.l, p, 32); return s; }
 
-// r*delta1, s*delta1, rs*delta1, s*delta2 depend only on (r, s): issued on a side stream before the MSMs
-static void launch_glue_pre(b2g_ctx* ctx, b2g_pk* pk, const void* r, const void* s) {
-    Scalar256 rr = load_scalar(r), ss = load_scalar(s);
-    CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_post, 0));      // d_pre of the previous proof is no longer read
-    glue_pre_kernel<<<1, 128, 0, ctx->st_glue>>>(pk->d_tab_delta1, pk->d_tab_delta2, rr, ss, ctx->d_pre);
+// (r, s) -> ctx->d_rs on stream 0.  Every entry point synchronises stream 0 before it returns (b2g_bench_device stages once),
+// so the pinned staging slot is free again by the time the next call overwrites it.
+static void stage_rs(b2g_ctx* ctx, const void* r, const void* s) {
+    memcpy(ctx->h_rs, r, 32); memcpy(ctx->h_rs + 32, s, 32);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_rs, ctx->h_rs, 64, cudaMemcpyHostToDevice, ctx->st[0]));
+    memcpy(ctx->pre_r, r, 32); memcpy(ctx->pre_s, s, 32);
+}
+
+// r*delta1, s*delta1, rs*delta1, s*delta2 depend only on (r, s): forked from stream 0 (after d_rs is written and after the
+// previous proof's assembly has read d_pre) onto a side stream, so they overlap the MSMs
+static void launch_glue_pre(b2g_ctx* ctx, b2g_pk* pk) {
+    CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->st[0]));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_fork, 0));
+    glue_pre_kernel<<<1, 192, 0, ctx->st_glue>>>(pk->d_tab_delta1, pk->d_tab_delta2, pk->d_tab_aa, pk->d_tab_bb, reinterpret_cast<const Scalar256*>(ctx->d_rs), ctx->d_pre);
     CUDA_CHECK(cudaEventRecord(ctx->ev_pre, ctx->st_glue));
-    memcpy(ctx->pre_r, rr.l, 32); memcpy(ctx->pre_s, ss.l, 32); ctx->pre_valid = true;
+    ctx->pre_valid = true;
     g_launch_count += 1;
 }
 
-static void launch_glue_post(b2g_ctx* ctx, b2g_pk* pk, const uint8_t* partials_dev, int count, const void* r, const void* s, cudaStream_t st) {
-    Scalar256 rr = load_scalar(r), ss = load_scalar(s);
+// scaled = true: records of REC_BYTES with [s*A_k, r*B1_k] behind the partial; false: bare 768-byte partials (host-mediated exchange)
+static void launch_glue_post(b2g_ctx* ctx, b2g_pk* pk, const uint8_t* partials_dev, int count, bool scaled, cudaStream_t st) {
     CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_pre, 0));
-    glue_post_kernel<<<1, 128, 0, st>>>(partials_dev, count, pk->d_consts, ctx->d_pre, rr, ss, ctx->d_proof);
-    CUDA_CHECK(cudaEventRecord(ctx->ev_post, st));
+    glue_post_kernel<<<1, 128, 0, st>>>(partials_dev, count, scaled ? (int)REC_BYTES : B2G_PARTIAL_BYTES, scaled ? B2G_PARTIAL_BYTES : -1, pk->d_consts, ctx->d_pre,
+                                        reinterpret_cast<const Scalar256*>(ctx->d_rs), ctx->d_proof);
     g_launch_count += 1;
     CUDA_CHECK(cudaGetLastError());
+}
+
+static unsigned long long p2p_timeout_ns() {
+    const char* v = getenv("B2G_P2P_TIMEOUT_MS");
+    long ms = v && *v ? strtol(v, nullptr, 10) : 20000;
+    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+}
+
+// Everything one proof does on the device between "witness and (r, s) are in HBM" and "proof bytes are in d_proof".
+// kind 0: whole proof; kind 1: base-sharded proof whose partials are exchanged through NVLink peer memory.
+static void enqueue_proof(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int kind, bool timed) {
+    cudaStream_t s0 = ctx->st[0];
+    launch_glue_pre(ctx, pk);
+    launch_msms(ctx, pk, mat, timed, true);
+    if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
+    if (kind == 1) {
+        xchg_publish_kernel<<<1, 64, 0, s0>>>(ctx->d_partial, ctx->d_xchg, ctx->d_epoch);
+        unsigned int* d_flag = reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES);       // local word after the two slots
+        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 4, s0));
+        xchg_gather_kernel<<<ctx->shard_count, 64, 0, s0>>>(ctx->d_peer_ptrs, ctx->shard_count, ctx->d_epoch, ctx->d_partials_all, p2p_timeout_ns(), d_flag);
+        g_launch_count += 2;
+        launch_glue_post(ctx, pk, ctx->d_partials_all, ctx->shard_count, true, s0);
+    } else {
+        launch_glue_post(ctx, pk, ctx->d_partial, 1, true, s0);
+    }
+}
+
+// Replays the captured pipeline (capturing it first if this context has none for (pk, mat)); falls back to direct launches
+// when graphs are disabled or the capture fails.
+static void run_proof(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int kind) {
+    cudaStream_t s0 = ctx->st[0];
+    if (!ctx->use_graph) { enqueue_proof(ctx, pk, mat, kind, true); return; }
+    const uint64_t key[3] = {pk->uid, mat->uid, ctx->alloc_gen};
+    if (ctx->gexec[kind] && memcmp(ctx->g_key[kind], key, sizeof key)) { cudaGraphExecDestroy(ctx->gexec[kind]); ctx->gexec[kind] = nullptr; }
+    if (!ctx->gexec[kind]) {
+        const uint64_t before = g_launch_count.load();
+        cudaGraph_t graph = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+        try { enqueue_proof(ctx, pk, mat, kind, false); }
+        catch (...) { cudaStreamEndCapture(s0, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); g_launch_count = before; throw; }
+        cudaError_t e = cudaStreamEndCapture(s0, &graph);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&ctx->gexec[kind], graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        ctx->g_launches[kind] = g_launch_count.load() - before;
+        g_launch_count = before;
+        if (e != cudaSuccess) {                       // not fatal: run this context without graphs from now on
+            cudaGetLastError();
+            ctx->gexec[kind] = nullptr; ctx->use_graph = false;
+            enqueue_proof(ctx, pk, mat, kind, true);
+            return;
+        }
+        memcpy(ctx->g_key[kind], key, sizeof key);
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev_t[10], s0)); CUDA_CHECK(cudaEventRecord(ctx->ev_t[11], s0));    // phase timers are not part of the graph:
+    for (int i = 0; i < 10; i++) CUDA_CHECK(cudaEventRecord(ctx->ev_t[i], s0));                         // they read as zero
+    CUDA_CHECK(cudaGraphLaunch(ctx->gexec[kind], s0));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
+    g_launch_count += ctx->g_launches[kind];
 }
 
 static void collect_timings(b2g_ctx* ctx) {
@@ -510,13 +655,19 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_w, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sort, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_post, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st_glue, cudaStreamNonBlocking));
         for (auto& e : ctx->ev_t) CUDA_CHECK(cudaEventCreate(&e));
-        CUDA_CHECK(cudaMalloc(&ctx->d_partial, B2G_PARTIAL_BYTES));
-        CUDA_CHECK(cudaMalloc(&ctx->d_partials_all, 64 * B2G_PARTIAL_BYTES));
+        CUDA_CHECK(cudaMalloc(&ctx->d_partial, REC_BYTES));
+        CUDA_CHECK(cudaMemset(ctx->d_partial, 0, REC_BYTES));
+        CUDA_CHECK(cudaMalloc(&ctx->d_partials_all, 64 * REC_BYTES));
         CUDA_CHECK(cudaMalloc(&ctx->d_proof, 256));
-        CUDA_CHECK(cudaMalloc(&ctx->d_pre, 3 * 128 + 256));
+        CUDA_CHECK(cudaMalloc(&ctx->d_pre, PRE_BYTES));
+        CUDA_CHECK(cudaMalloc(&ctx->d_rs, 64));
+        CUDA_CHECK(cudaMallocHost(&ctx->h_rs, 64));
+        CUDA_CHECK(cudaMalloc(&ctx->d_epoch, 8));
+        CUDA_CHECK(cudaMemset(ctx->d_epoch, 0, 8));
+        { const char* g = getenv("B2G_GRAPH"); ctx->use_graph = !(g && *g == '0'); }
         CUDA_CHECK(cudaMalloc(&ctx->d_xchg, XCHG_BYTES + 256));            // plain cudaMalloc: exportable through CUDA IPC
         CUDA_CHECK(cudaMemset(ctx->d_xchg, 0, XCHG_BYTES + 256));
         CUDA_CHECK(cudaMalloc(&ctx->d_peer_ptrs, 64 * sizeof(uint8_t*)));
@@ -531,7 +682,11 @@ int b2g_ctx_destroy(b2g_ctx* ctx) {
         DevGuard g(ctx->device);
         cudaDeviceSynchronize();
         for (int i = 0; i < NQ; i++) { if (ctx->scratch_ok) msm_scratch_free(ctx->scratch[i]); cudaStreamDestroy(ctx->st[i]); cudaEventDestroy(ctx->ev_done[i]); }
-        cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_post); cudaStreamDestroy(ctx->st_glue);
+        cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_fork); cudaStreamDestroy(ctx->st_glue);
+        for (auto& g : ctx->gexec) if (g) cudaGraphExecDestroy(g);
+        if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
+        if (ctx->d_rs) cudaFree(ctx->d_rs);
+        if (ctx->d_epoch) cudaFree(ctx->d_epoch);
         for (auto& e : ctx->ev_t) cudaEventDestroy(e);
         for (int k = 0; k < 64; k++) if (ctx->peer_mapped[k]) cudaIpcCloseMemHandle(ctx->peer_mapped[k]);
         for (void* p : {(void*)ctx->d_xchg, (void*)ctx->d_peer_ptrs, (void*)ctx->d_partial, (void*)ctx->d_partials_all, (void*)ctx->d_proof, (void*)ctx->d_pre, (void*)ctx->d_w,
@@ -591,9 +746,16 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
         msm_validate_points(pk->d_consts + 5 * 64, 3, true, st, "beta_g2 / delta_g2 / b_g2_query[0]");
         CUDA_CHECK(cudaMalloc(&pk->d_tab_delta1, 32 * 255 * 64));
         CUDA_CHECK(cudaMalloc(&pk->d_tab_delta2, 32 * 255 * 128));
+        CUDA_CHECK(cudaMalloc(&pk->d_tab_aa, 32 * 255 * 64 + 64));
+        CUDA_CHECK(cudaMalloc(&pk->d_tab_bb, 32 * 255 * 64 + 64));
         fixed_table_kernel<G1, Fq><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_delta1, pk->d_consts + 2 * 64);
         fixed_table_kernel<G2, Fq2><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_delta2, pk->d_consts + 5 * 64 + 128);
-        g_launch_count += 2;
+        // alpha1 + a_query[0] and beta1 + b_g1_query[0] (affine sums parked behind their tables), then their window tables
+        affine_sum_kernel<<<1, 1, 0, st>>>(pk->d_consts, 0, 3, (uint8_t*)pk->d_tab_aa + 32 * 255 * 64);
+        affine_sum_kernel<<<1, 1, 0, st>>>(pk->d_consts, 1, 4, (uint8_t*)pk->d_tab_bb + 32 * 255 * 64);
+        fixed_table_kernel<G1, Fq><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_aa, (uint8_t*)pk->d_tab_aa + 32 * 255 * 64);
+        fixed_table_kernel<G1, Fq><<<(32 * 255 + 63) / 64, 64, 0, st>>>(pk->d_tab_bb, (uint8_t*)pk->d_tab_bb + 32 * 255 * 64);
+        g_launch_count += 6;
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaStreamSynchronize(st));
         guard.pk = nullptr;
@@ -696,7 +858,6 @@ static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_m
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[12], s0));
     CUDA_CHECK(cudaMemcpyAsync(ctx->d_w, w_mont, (size_t)mat->n_vars * 32, cudaMemcpyHostToDevice, s0));
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[13], s0));
-    launch_msms(ctx, pk, mat, true);
 }
 
 int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, uint8_t proof_out[256]) {
@@ -705,11 +866,11 @@ int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const
         if (ctx->shard_count != 1) throw_error(B2G_E_SHAPE, "b2g_prove needs an unsharded context; use b2g_prove_partial/finish");
         DevGuard g(ctx->device);
         check_shapes(ctx, pk, mat);
-        launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
+        stage_rs(ctx, r_canon, s_canon);
         cudaStream_t s0 = ctx->st[0];
-        CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
-        launch_glue_post(ctx, pk, ctx->d_partial, 1, r_canon, s_canon, s0);
+        run_proof(ctx, pk, mat, 0);
+        ctx->pre_valid = false;
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
@@ -723,8 +884,9 @@ int b2g_prove_partial(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_cano
         DevGuard g(ctx->device);
         check_shapes(ctx, pk, mat);
         ctx->pre_valid = false;
-        if (r_canon && s_canon) launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
+        if (r_canon && s_canon) { stage_rs(ctx, r_canon, s_canon); launch_glue_pre(ctx, pk); }
+        launch_msms(ctx, pk, mat, true, false);
         cudaStream_t s0 = ctx->st[0];
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
         CUDA_CHECK(cudaMemcpyAsync(partial_out, ctx->d_partial, B2G_PARTIAL_BYTES, cudaMemcpyDeviceToHost, s0));
@@ -741,10 +903,10 @@ int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all, int cou
         check_pk_ctx(ctx, pk);
         DevGuard g(ctx->device);
         cudaStream_t s0 = ctx->st[0];
-        if (!(ctx->pre_valid && !memcmp(ctx->pre_r, r_canon, 32) && !memcmp(ctx->pre_s, s_canon, 32))) launch_glue_pre(ctx, pk, r_canon, s_canon);
+        if (!(ctx->pre_valid && !memcmp(ctx->pre_r, r_canon, 32) && !memcmp(ctx->pre_s, s_canon, 32))) { stage_rs(ctx, r_canon, s_canon); launch_glue_pre(ctx, pk); }
         ctx->pre_valid = false;
         CUDA_CHECK(cudaMemcpyAsync(ctx->d_partials_all, partials_all, (size_t)count * B2G_PARTIAL_BYTES, cudaMemcpyHostToDevice, s0));
-        launch_glue_post(ctx, pk, ctx->d_partials_all, count, r_canon, s_canon, s0);
+        launch_glue_post(ctx, pk, ctx->d_partials_all, count, false, s0);
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
     });
@@ -789,12 +951,6 @@ int b2g_p2p_import(b2g_ctx* ctx, const void* handles_all, int count) {
     });
 }
 
-static unsigned long long p2p_timeout_ns() {
-    const char* v = getenv("B2G_P2P_TIMEOUT_MS");
-    long ms = v && *v ? strtol(v, nullptr, 10) : 20000;
-    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
-}
-
 int b2g_p2p_connect_local(b2g_ctx** ctxs, int count) {
     return guarded([&] {
         if (!ctxs || count < 1 || count > 64) throw_error(B2G_E_SHAPE, "bad arguments");
@@ -820,18 +976,12 @@ int b2g_prove_sharded_p2p(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_
         if (ctx->peers_imported != ctx->shard_count) throw_error(B2G_E_SHAPE, "b2g_p2p_import has not been called with every rank's handle");
         DevGuard g(ctx->device);
         check_shapes(ctx, pk, mat);
-        launch_glue_pre(ctx, pk, r_canon, s_canon);
         prove_common(ctx, pk, mat, w_mont);
+        stage_rs(ctx, r_canon, s_canon);
         cudaStream_t s0 = ctx->st[0];
-        CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
-        const unsigned long long epoch = ++ctx->epoch;
-        xchg_publish_kernel<<<1, 64, 0, s0>>>(ctx->d_partial, ctx->d_xchg, epoch);
-        unsigned int* d_flag = reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES);       // local word after the two slots
-        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 4, s0));
-        xchg_gather_kernel<<<ctx->shard_count, 64, 0, s0>>>(ctx->d_peer_ptrs, ctx->shard_count, epoch, ctx->d_partials_all,
-                                                            p2p_timeout_ns(), d_flag);
-        g_launch_count += 2;
-        launch_glue_post(ctx, pk, ctx->d_partials_all, ctx->shard_count, r_canon, s_canon, s0);
+        run_proof(ctx, pk, mat, 1);
+        ctx->pre_valid = false;
+        unsigned int* d_flag = reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES);
         unsigned int flag = 0;
         CUDA_CHECK(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, s0));
         CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
@@ -853,13 +1003,10 @@ int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* a
         // representative full-size scalars (the glue cost depends on their bit length)
         Scalar256 kr = {{0x90abcdefu, 0x12345678u, 0x90abcdefu, 0x12345678u, 0x0badc0deu, 0x0defaced, 0x13572468u, 0x1fedcba9u}};
         Scalar256 ks = {{0x87654321u, 0xfedcba09u, 0x87654321u, 0xfedcba09u, 0x600dcafeu, 0x0ddba11u, 0x24681357u, 0x2abcdef0u}};
+        stage_rs(ctx, kr.l, ks.l);
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[16], s0));
-        for (int it = 0; it < iters; it++) {
-            CUDA_CHECK(cudaStreamWaitEvent(ctx->st_glue, ctx->ev_t[16], 0));
-            launch_glue_pre(ctx, pk, kr.l, ks.l);
-            launch_msms(ctx, pk, mat, false);
-            launch_glue_post(ctx, pk, ctx->d_partial, 1, kr.l, ks.l, s0);
-        }
+        for (int it = 0; it < iters; it++) run_proof(ctx, pk, mat, 0);
+        ctx->pre_valid = false;
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[17], s0));
         CUDA_CHECK(cudaStreamSynchronize(s0));
         float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t[16], ctx->ev_t[17]));

@@ -189,6 +189,59 @@ def test_msm_small_chunks_exercise_fragments(ctx, monkeypatch):
         assert np.array_equal(ctx.msm_g1(bases, scl), exp), chunk
 
 
+@pytest.mark.parametrize('rounds', ['1', '2', '3', '6'])
+def test_msm_batched_affine_levels(ctx, monkeypatch, rounds):
+    """The batched-affine pre-reduction (msm.cu 4a: R levels of pairwise affine additions inside the buckets, inversions shared
+    by Montgomery's trick) forced on at small sizes, G1 and G2, against oracle/cref.c: uniform and circom-like scalars (one
+    300-entry bucket next to near-empty ones), more levels than the largest bucket can be halved, points at infinity in the
+    table, and tiny chunks of the final XYZZ stage."""
+    monkeypatch.setenv('B2G_MSM_AFFINE_ROUNDS', rounds)
+    rng = random.Random(1000 + int(rounds))
+    for n, dist in ((1, 'uniform'), (2, 'ones'), (37, 'uniform'), (3000, 'circomlike'), (20000, 'uniform'), (20000, 'same')):
+        ks, sc = _msm_case(rng, n, dist)
+        bases = c.fixed_base_g1(c.ints_to_limbs(ks))
+        if n > 40:
+            bases[5] = 0; bases[9] = bases[8]; sc[8] = 5; sc[9] = o.R_MOD - 5; sc[0] = 0; sc[1] = 1; sc[2] = o.R_MOD - 1
+        scl = c.ints_to_limbs(sc)
+        assert np.array_equal(ctx.msm_g1(bases, scl), c.msm_g1(bases, scl)), (n, dist)
+    for n, dist in ((3, 'ones'), (700, 'circomlike'), (6000, 'uniform')):
+        ks, sc = _msm_case(rng, n, dist)
+        bases = c.fixed_base_g2(c.ints_to_limbs(ks))
+        if n > 40:
+            bases[5] = 0; bases[9] = bases[8]; sc[8] = 5; sc[9] = o.R_MOD - 5
+        scl = c.ints_to_limbs(sc)
+        assert np.array_equal(ctx.msm_g2(bases, scl), c.msm_g2(bases, scl)), (n, dist)
+    monkeypatch.setenv('B2G_MSM_CHUNK', '3')
+    ks, sc = _msm_case(rng, 5000, 'circomlike')
+    bases = c.fixed_base_g1(c.ints_to_limbs(ks)); scl = c.ints_to_limbs(sc)
+    assert np.array_equal(ctx.msm_g1(bases, scl), c.msm_g1(bases, scl))
+
+
+def test_msm_batched_affine_exceptional_pairs(ctx, monkeypatch):
+    """Buckets that hold exactly two points make the pairing deterministic: P + P (the doubling branch of the affine
+    addition), P + (-P) (sum at infinity, denominator replaced by one) and P + infinity."""
+    monkeypatch.setenv('B2G_MSM_AFFINE_ROUNDS', '2')
+    rng = random.Random(4242)
+    k = rng.randrange(1, o.R_MOD)
+    P = c.fixed_base_g1(c.ints_to_limbs([k]))[0]
+    Pn = c.fixed_base_g1(c.ints_to_limbs([o.R_MOD - k]))[0]                    # -P
+    inf = np.zeros_like(P)
+    for sv in (1, 5, rng.randrange(o.R_MOD), o.R_MOD - 1):
+        scl = c.ints_to_limbs([sv, sv])
+        for pair in ((P, P), (P, Pn), (P, inf), (inf, P), (inf, inf)):
+            bases = np.stack(pair)
+            assert np.array_equal(ctx.msm_g1(bases, scl), c.msm_g1(bases, scl)), sv
+    Q = c.fixed_base_g2(c.ints_to_limbs([k]))[0]
+    Qn = c.fixed_base_g2(c.ints_to_limbs([o.R_MOD - k]))[0]
+    scl = c.ints_to_limbs([7, 7])
+    for pair in ((Q, Q), (Q, Qn), (Q, np.zeros_like(Q))):
+        bases = np.stack(pair)
+        assert np.array_equal(ctx.msm_g2(bases, scl), c.msm_g2(bases, scl))
+    # four equal points: level 1 doubles twice, level 2 doubles the doubles
+    bases = np.stack((P, P, P, P)); scl = c.ints_to_limbs([3, 3, 3, 3])
+    assert np.array_equal(ctx.msm_g1(bases, scl), c.msm_g1(bases, scl))
+
+
 def test_msm_truncation_rule(ctx):
     rng = random.Random(3)
     bases = c.fixed_base_g1(c.ints_to_limbs([rng.randrange(1, o.R_MOD) for _ in range(50)]))
