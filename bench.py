@@ -294,9 +294,24 @@ def run_ours(args):
             return sharding.prove_sharded(ctxs[i], pk, cm, wl.wms[i], R_FIX, S_FIX, dist, dev, None)
 
         from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=inflight)          # persistent host threads: one per in-flight proof
+        use_async = (not sharded) and args.host_driver == 'async'
+        pool = ThreadPoolExecutor(max_workers=inflight)          # 'threads' driver: one host thread per in-flight proof
 
         def run_steps(total):
+            if use_async:
+                # ONE host thread keeps `inflight` proofs queued (b2g_prove_submit / b2g_prove_wait, one Context each):
+                # every step still uploads its witness from pinned host memory and reads its 256 proof bytes back
+                pend, submitted, done, last = [None] * inflight, 0, 0, None
+                def submit(j):
+                    return Groth16.submit(pk, R_FIX, S_FIX, cm, wl.wms[j], ctxs[j])
+                for j in range(min(inflight, total)):
+                    pend[j] = submit(j); submitted += 1
+                while done < total:
+                    j = done % inflight
+                    last = pend[j].wait(); done += 1
+                    if submitted < total:
+                        pend[j] = submit(j); submitted += 1
+                return last
             def worker(i):
                 last = None
                 for _ in range(total // inflight + (1 if i < total % inflight else 0)):
@@ -320,7 +335,9 @@ def run_ours(args):
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         launches = ctxs[0].launch_count() - launches0
-        res = {"mode": mode, "proof": proof, "launches": launches, "e2e_s": e2e_s, "ctxs": ctxs, "inflight": inflight}
+        res = {"mode": mode, "proof": proof, "launches": launches, "e2e_s": e2e_s, "ctxs": ctxs, "inflight": inflight,
+               "host_driver": ("one host thread, b2g_prove_submit/wait" if use_async else f"{inflight} host threads, synchronous b2g_prove") + "; one captured CUDA graph launch per proof",
+               "host_ms_last_proof": {k: v for k, v in ctxs[0].last_timings().items() if k.startswith('host_') or k in ('h2d', 'total')}}
         per_step = world if mode == 'replicas' else 1                    # replicas: every rank proves its own copy
         res["e2e_value"] = per_step * steps / e2e_s
         if not sharded:
@@ -469,7 +486,7 @@ def run_ours(args):
                "clocks": main["clocks"],
                "e2e": {"value": main["e2e_value"], "unit": "proofs/s", "h2d_bytes_per_step": n_vars * 32 + 64 + (768 * world if sharded and args.exchange != 'p2p' else 0),
                        "d2h_bytes_per_step": 256 + (768 * (world + 1) if sharded and args.exchange != 'p2p' else 0), "ms_per_step": 1e3 * main["e2e_s"] / args.steps,
-                       "host_driver": f"{main['inflight']} host threads, one Context each; one captured CUDA graph launch per proof"},
+                       "host_driver": main["host_driver"], "host_ms_last_proof": main["host_ms_last_proof"]},
                "gpu_launches": main["launches"], "roofline": roof, "cpu_baseline": cpu}
         out.update(extra)
         if other:
@@ -510,6 +527,7 @@ def main():
     ap.add_argument('--no-config4', action='store_true', help='N>1: skip the 2^22 base-sharded leg (BASELINE.json config 4)')
     ap.add_argument('--steps4', type=int, default=5, help='timed proofs of the 2^22 leg')
     ap.add_argument('--inflight', type=int, default=3, help='proofs in flight per GPU (one Context + host thread each)')
+    ap.add_argument('--host-driver', default='async', choices=['async', 'threads'], help="e2e loop: one host thread with b2g_prove_submit/wait (async) or one thread per in-flight proof")
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--skip-check', action='store_true')
     args = ap.parse_args()

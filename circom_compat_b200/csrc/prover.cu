@@ -6,6 +6,7 @@
 //     streams 1..4: MSMs over l_query / a_query[1..] / b_g1_query[1..] / b_g2_query[1..] against the witness
 //     stream 0: glue (r*delta, s*delta, vk terms, s*A + r*B1 - rs*delta + L + H, three affine conversions) -> D2H 256 B
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <vector>
 #include "../../include/b2groth.h"
@@ -49,6 +50,7 @@ struct b2g_ctx {
     float last_ms[16] = {};
     bool pre_valid = false; uint32_t pre_r[8] = {}, pre_s[8] = {};   // (r, s) whose glue_pre result sits in d_pre
     uint8_t *d_rs = nullptr, *h_rs = nullptr;  // r | s (canonical, 2 x 32 B): device copy read by the glue kernels, pinned staging
+    uint8_t *h_proof = nullptr, *pending_out = nullptr;   // pinned landing slot of the proof bytes; caller's buffer of a submitted proof
     // One proof's whole device pipeline (all streams, ~100 launches) captured once per (key, matrices) as a CUDA graph and
     // replayed with a single launch: the host cost of a proof drops from ~130 driver calls to a handful (B2G_GRAPH=0 disables)
     bool use_graph = true;
@@ -665,9 +667,12 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         CUDA_CHECK(cudaMalloc(&ctx->d_pre, PRE_BYTES));
         CUDA_CHECK(cudaMalloc(&ctx->d_rs, 64));
         CUDA_CHECK(cudaMallocHost(&ctx->h_rs, 64));
+        CUDA_CHECK(cudaMallocHost(&ctx->h_proof, 256));
         CUDA_CHECK(cudaMalloc(&ctx->d_epoch, 8));
         CUDA_CHECK(cudaMemset(ctx->d_epoch, 0, 8));
         { const char* g = getenv("B2G_GRAPH"); ctx->use_graph = !(g && *g == '0'); }
+        // tuning knob: L2 -> DRAM fetch granularity hint (bytes: 32 / 64 / 128) for the 64-byte table gathers (profiles/r2_load_width.md)
+        { const char* g = getenv("B2G_L2_FETCH"); if (g && *g) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)strtol(g, nullptr, 10)); cudaGetLastError(); }
         CUDA_CHECK(cudaMalloc(&ctx->d_xchg, XCHG_BYTES + 256));            // plain cudaMalloc: exportable through CUDA IPC
         CUDA_CHECK(cudaMemset(ctx->d_xchg, 0, XCHG_BYTES + 256));
         CUDA_CHECK(cudaMalloc(&ctx->d_peer_ptrs, 64 * sizeof(uint8_t*)));
@@ -685,6 +690,7 @@ int b2g_ctx_destroy(b2g_ctx* ctx) {
         cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_fork); cudaStreamDestroy(ctx->st_glue);
         for (auto& g : ctx->gexec) if (g) cudaGraphExecDestroy(g);
         if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
+        if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
         if (ctx->d_rs) cudaFree(ctx->d_rs);
         if (ctx->d_epoch) cudaFree(ctx->d_epoch);
         for (auto& e : ctx->ev_t) cudaEventDestroy(e);
@@ -860,21 +866,64 @@ static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_m
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[13], s0));
 }
 
+static double host_ms_since(const std::chrono::steady_clock::time_point& t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// enqueue one whole proof; nothing here waits for the device (the witness must be page-locked for the upload to be
+// asynchronous too; the 256 proof bytes come back through the context's own pinned slot)
+static void prove_submit(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, uint8_t* proof_out) {
+    if (!ctx || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
+    if (ctx->shard_count != 1) throw_error(B2G_E_SHAPE, "b2g_prove needs an unsharded context; use b2g_prove_partial/finish");
+    if (ctx->pending_out) throw_error(B2G_E_SHAPE, "a submitted proof is still pending on this context: call b2g_prove_wait first");
+    const auto t0 = std::chrono::steady_clock::now();
+    check_shapes(ctx, pk, mat);
+    prove_common(ctx, pk, mat, w_mont);
+    stage_rs(ctx, r_canon, s_canon);
+    ctx->last_ms[9] = (float)host_ms_since(t0);
+    cudaStream_t s0 = ctx->st[0];
+    run_proof(ctx, pk, mat, 0);
+    ctx->pre_valid = false;
+    CUDA_CHECK(cudaMemcpyAsync(ctx->h_proof, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
+    ctx->pending_out = proof_out;
+    ctx->last_ms[10] = (float)host_ms_since(t0);
+}
+
+static void prove_wait(b2g_ctx* ctx) {
+    if (!ctx) throw_error(B2G_E_SHAPE, "null pointer");
+    if (!ctx->pending_out) throw_error(B2G_E_SHAPE, "no submitted proof is pending on this context");
+    const auto t0 = std::chrono::steady_clock::now();
+    uint8_t* out = ctx->pending_out;
+    ctx->pending_out = nullptr;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->st[0]));
+    memcpy(out, ctx->h_proof, 256);
+    ctx->last_ms[11] = (float)host_ms_since(t0);
+    collect_timings(ctx);
+}
+
 int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, uint8_t proof_out[256]) {
     return guarded([&] {
-        if (!ctx || !r_canon || !s_canon || !proof_out) throw_error(B2G_E_SHAPE, "null pointer");
-        if (ctx->shard_count != 1) throw_error(B2G_E_SHAPE, "b2g_prove needs an unsharded context; use b2g_prove_partial/finish");
+        if (!ctx) throw_error(B2G_E_SHAPE, "null pointer");
         DevGuard g(ctx->device);
-        check_shapes(ctx, pk, mat);
-        prove_common(ctx, pk, mat, w_mont);
-        stage_rs(ctx, r_canon, s_canon);
-        cudaStream_t s0 = ctx->st[0];
-        run_proof(ctx, pk, mat, 0);
-        ctx->pre_valid = false;
-        CUDA_CHECK(cudaMemcpyAsync(proof_out, ctx->d_proof, 256, cudaMemcpyDeviceToHost, s0));
-        CUDA_CHECK(cudaEventRecord(ctx->ev_t[15], s0));
-        CUDA_CHECK(cudaStreamSynchronize(s0));
-        collect_timings(ctx);
+        prove_submit(ctx, pk, mat, r_canon, s_canon, w_mont, proof_out);
+        prove_wait(ctx);
+    });
+}
+
+int b2g_prove_submit(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont, uint8_t proof_out[256]) {
+    return guarded([&] {
+        if (!ctx) throw_error(B2G_E_SHAPE, "null pointer");
+        DevGuard g(ctx->device);
+        prove_submit(ctx, pk, mat, r_canon, s_canon, w_mont, proof_out);
+    });
+}
+
+int b2g_prove_wait(b2g_ctx* ctx) {
+    return guarded([&] {
+        if (!ctx) throw_error(B2G_E_SHAPE, "null pointer");
+        DevGuard g(ctx->device);
+        prove_wait(ctx);
     });
 }
 

@@ -114,8 +114,8 @@ class Context:
     def last_timings(self) -> dict:
         buf = (C.c_float * 16)()
         N.check(N.lib().b2g_last_timings(self._h, buf))
-        names = ('h2d', 'witness_map', 'msm_h', 'msm_l', 'msm_a', 'msm_b1', 'msm_b2', 'glue_d2h', 'total')
-        return dict(zip(names, list(buf)[:9]))
+        names = ('h2d', 'witness_map', 'msm_h', 'msm_l', 'msm_a', 'msm_b1', 'msm_b2', 'glue_d2h', 'total', 'host_upload_enqueued', 'host_all_enqueued', 'host_wait')
+        return dict(zip(names, list(buf)[:12]))
 
     def bench_device(self, pk, matrices, iters: int) -> float:
         """average CUDA-event ms of witness map + 5 MSMs + glue with the witness already resident in HBM"""
@@ -210,6 +210,18 @@ class Proof:
         return (self._int(6), self._int(7))
 
 
+class PendingProof:
+    """A proof submitted with Groth16.submit; keeps the witness and output buffers alive until wait()."""
+
+    def __init__(self, ctx, out, w):
+        self._ctx, self._out, self._w = ctx, out, w
+
+    def wait(self) -> Proof:
+        N.check(N.lib().b2g_prove_wait(self._ctx._h))
+        self._w = None
+        return Proof(self._out.tobytes())
+
+
 def _scalar_bytes(v) -> np.ndarray:
     if isinstance(v, (int, np.integer)):
         return np.frombuffer((int(v) % R_MOD).to_bytes(32, 'little'), dtype='<u8').copy()
@@ -282,6 +294,19 @@ class Groth16:
         out = np.zeros(256, dtype=np.uint8)
         N.check(N.lib().b2g_prove(ctx._h, ph, mh, _ptr(rr), _ptr(ss), _ptr(w), _ptr(out)))
         return Proof(out.tobytes())
+
+    @staticmethod
+    def submit(pk: ProvingKey, r, s, matrices: ConstraintMatrices, full_assignment, ctx: Context, reduction=CircomReduction) -> 'PendingProof':
+        """create_proof_with_reduction_and_matrices without the wait: enqueues the proof on `ctx` (one pending proof per
+        context) and returns a handle whose .wait() yields the Proof.  One host thread + K contexts = K proofs in flight."""
+        w = _c(full_assignment)
+        if w.size // 4 != pk.n_vars:
+            raise ValueError("full_assignment length != n_vars")
+        ph, mh = ctx.pk_handle(pk), ctx.mat_handle(matrices, pk.n_vars, reduction.ID)
+        rr, ss = _scalar_bytes(r), _scalar_bytes(s)
+        out = np.zeros(256, dtype=np.uint8)
+        N.check(N.lib().b2g_prove_submit(ctx._h, ph, mh, _ptr(rr), _ptr(ss), _ptr(w), _ptr(out)))
+        return PendingProof(ctx, out, w)
 
     @staticmethod
     def prove(pk: ProvingKey, matrices: ConstraintMatrices, full_assignment, rng, ctx: Context = None, reduction=CircomReduction) -> Proof:

@@ -120,6 +120,16 @@ B2G_API int b2g_witness_map(b2g_ctx* ctx, b2g_mat* mat, const void* w_mont, void
 B2G_API int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont,
               uint8_t proof_out[256]);
 
+/* The same call split in two so that ONE host thread can keep several proofs in flight (one b2g_ctx each): submit
+ * enqueues the upload, the captured proof graph and the read-back and returns without waiting for the device (w_mont
+ * should be page-locked, or the upload is synchronous); wait blocks until that proof is done and fills the proof_out
+ * given to submit, which must stay valid until then.  At most one proof may be pending per context.
+ * b2g_prove == submit + wait.  (Reference shape: a rayon/thread pool calling the synchronous prove; here the pipeline is
+ * a property of the device queue, not of host threads.) */
+B2G_API int b2g_prove_submit(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont,
+                             uint8_t proof_out[256]);
+B2G_API int b2g_prove_wait(b2g_ctx* ctx);
+
 /* Sharded proof.  partial_out (768 B, host or device-accessible host memory) = this rank's partial MSM results
  * [H, L, A, B1] as G1 XYZZ (128 B each) followed by B2 as G2 XYZZ (256 B), mont.  b2g_prove_finish folds
  * shard_count partials in rank order and assembles the proof; every rank obtains identical bytes. */
@@ -162,7 +172,10 @@ B2G_API int b2g_test_op(b2g_ctx* ctx, int op, const void* a, const void* b, size
 
 /* Timing of the last b2g_prove / b2g_prove_partial on this ctx, CUDA-event milliseconds:
  * [0] h2d witness, [1] witness map, [2] msm H, [3] msm L, [4] msm A, [5] msm B1, [6] msm B2, [7] glue + d2h,
- * [8] whole call (first event to last event). */
+ * [8] whole call (first event to last event).  With the captured proof graph (default) [1]..[6] read 0: the graph has no
+ * interior events (B2G_GRAPH=0 in the environment at b2g_ctx_create restores direct launches and the per-phase times).
+ * Host wall-clock milliseconds of the same call: [9] entry -> upload enqueued, [10] entry -> everything enqueued,
+ * [11] time blocked in the final wait. */
 B2G_API int b2g_last_timings(b2g_ctx* ctx, float out_ms[16]);
 
 /* Benchmark helper: the device-resident part of a proof (witness already in HBM from the last b2g_prove call):

@@ -330,6 +330,32 @@ def test_synthetic_proof_vs_oracle_and_trapdoor(ctx, kind, log_n):
     assert synth.expected_proof_dlogs_independent(td, circ, w, r, s) == (da, db, dc)
 
 
+def test_submit_wait_pipelines_proofs_on_one_thread(golden, complex_zkey_bytes):
+    """b2g_prove_submit / b2g_prove_wait: three contexts, one host thread, proofs with different (r, s) in flight at once
+    (the captured proof graph is replayed with new r, s and witness each time); results equal the synchronous call's."""
+    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, Context, B2gError
+    pk, cm = read_zkey(complex_zkey_bytes)
+    g = golden['complex_zkey']
+    wm = fr_to_mont(o.chain_witness(pk.n_vars, g['a']))
+    ctxs = [Context(0) for _ in range(3)]
+    rs = [(int(g['r']), int(g['s'])), (5, 7), (0, 11), (o.R_MOD - 1, 3), (int(g['r']), int(g['s'])), (1, 0)]
+    expect = [Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, cm.num_instance_variables, cm.num_constraints, wm, ctxs[0]).data for r, s in rs]
+    assert expect[0].hex() == g['proof_hex'] and expect[4] == expect[0] and len(set(expect)) == 5
+    pend, got = {}, []
+    for k, (r, s) in enumerate(rs):
+        j = k % 3
+        if j in pend:
+            got.append(pend.pop(j).wait().data)
+        pend[j] = Groth16.submit(pk, r, s, cm, wm, ctxs[j])
+    with pytest.raises(B2gError):                                  # one pending proof per context
+        Groth16.submit(pk, 1, 1, cm, wm, ctxs[0])
+    for j in (0, 1, 2):
+        got.append(pend.pop(j).wait().data)
+    assert got == expect
+    for cx in ctxs:
+        cx.close()
+
+
 def test_sharded_proof_equals_whole_proof(golden, complex_zkey_bytes):
     # base-range sharding on one device: 3 shard contexts, partials folded in rank order
     from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, Context
