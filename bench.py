@@ -282,8 +282,8 @@ def run_ours(args):
         ctxs = [Context(local, rank if sharded else 0, world if sharded else 1) for _ in range(inflight)]
         fused = sharded and args.exchange == 'p2p'
         if fused:
-            sharding.connect_p2p(ctxs[0], dist)                    # CUDA-IPC handles of the exchange buffers, once
-            ctxs[0].prepare(pk, cm)
+            ctxs[0].prepare(pk, cm)                                # sizes the exchange arena (split witness map) before it is exported
+            sharding.connect_p2p(ctxs[0], dist)                    # CUDA-IPC handles of the exchange arenas, once
             dist.barrier()
 
         def one_proof(i=0):

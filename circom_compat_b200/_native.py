@@ -10,6 +10,7 @@ LIB_PATH = os.environ.get('B2G_LIB') or os.path.join(_HERE, 'libb2groth.so')   #
 
 B2G_OK, B2G_E_DOMAIN, B2G_E_SHAPE, B2G_E_DEVICE, B2G_E_INPUT = 0, -1, -2, -3, -4
 PARTIAL_BYTES = 768
+IPC_HANDLE_BYTES = 80          # B2G_IPC_HANDLE_BYTES: cudaIpcMemHandle_t + arena capacity
 REDUCTION_CIRCOM, REDUCTION_LIBSNARK = 0, 1
 
 

@@ -294,6 +294,16 @@ void ntt_witness_transform(const NttDomain& d, fe* a, fe* b, fe* c, fe* out, cud
     CUDA_CHECK(cudaGetLastError());
 }
 
+// ONE vector through the same chain, in place and without the pointwise step: evaluations on H (natural order) ->
+// coefficients -> evaluations on the coset g*H (natural order).  Used when the three transforms of a proof run on three
+// different GPUs (prover.cu, sharded proofs) and h = a*b - c is formed from peer memory afterwards.
+void ntt_transform_single(const NttDomain& d, fe* v, cudaStream_t st) {
+    for (int p = d.npass - 1; p >= 1; p--) launch_pass(d, v, nullptr, nullptr, 1, nullptr, p, 1, 0, 0, 0, st);
+    launch_pass(d, v, nullptr, nullptr, 1, nullptr, 0, 1, 1, 1, 0, st);
+    for (int p = 1; p < d.npass; p++) launch_pass(d, v, nullptr, nullptr, 1, nullptr, p, 0, 0, 1, 0, st);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // LibsnarkReduction::witness_map_from_matrices (ark-groth16 0.5.0 r1cs_to_qap.rs, the default QAP of Groth16<Bn254> used by
 // /root/reference/tests/groth16.rs): a, b, c (c from the real C matrix) -> coefficients -> evaluations on the coset
 // g*H (g = 5) -> (a*b - c) / Z(g) -> coset iFFT -> the n coefficients of h, natural order, in `out`.

@@ -17,6 +17,7 @@ struct NttDomain {
 void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark = false);
 void ntt_domain_destroy(NttDomain& d);
 void ntt_witness_transform(const NttDomain& d, fe* a, fe* b, fe* c, fe* out, cudaStream_t st);
+void ntt_transform_single(const NttDomain& d, fe* v, cudaStream_t st);
 void ntt_witness_transform_libsnark(const NttDomain& d, fe* a, fe* b, fe* c, fe* scratch, fe* out, cudaStream_t st);
 void ntt_plain(const NttDomain& d, fe* data, fe* tmp, bool inverse, cudaStream_t st);
 void spmv_launch(uint32_t n, uint32_t m, uint32_t num_inputs, const uint32_t* a_rowptr, const uint32_t* a_col, const fe* a_val,

@@ -36,7 +36,7 @@ static const size_t PARTIAL_OFF[NQ] = {0, 128, 256, 384, 512};
 using namespace b2g;
 
 struct b2g_ctx {
-    int device = 0, shard_rank = 0, shard_count = 1;
+    int device = 0, shard_rank = 0, shard_count = 1, stream_priority = 0;
     cudaStream_t st[NQ] = {}, st_glue = nullptr;
     cudaEvent_t ev_w = nullptr, ev_sort = nullptr, ev_pre = nullptr, ev_fork = nullptr, ev_done[NQ] = {}, ev_t[20] = {};
     MsmScratch scratch[NQ];
@@ -60,7 +60,8 @@ struct b2g_ctx {
     uint64_t g_launches[2] = {0, 0};
     unsigned long long* d_epoch = nullptr;                     // exchange epoch (device-resident so that it survives graph replay)
     // peer-memory exchange (b2g_prove_sharded_p2p): own buffer + every rank's buffer as seen from this device
-    uint8_t* d_xchg = nullptr;                 // XCHG_BYTES: 2 slots x {epoch u64 @0, partial @256}
+    uint8_t* d_xchg = nullptr;                 // exchange arena (layout at EVAL_OFF below); allocated when the context is wired to its peers
+    size_t eval_cap = 0, eval_common = 0;      // field elements the own arena holds / the smallest arena among all ranks
     uint8_t** d_peer_ptrs = nullptr;           // device array [shard_count]
     void* peer_mapped[64] = {};                // cudaIpcOpenMemHandle results (to close)
     int peers_imported = 0;
@@ -248,6 +249,14 @@ __global__ void glue_post_kernel(const uint8_t* __restrict__ partials, int count
 constexpr size_t REC_BYTES = B2G_PARTIAL_BYTES + 256;  // device-side record of one rank: the public 768-byte partial + [s*A_k, r*B1_k]
 constexpr size_t XCHG_SLOT = 256 + REC_BYTES;         // epoch word at +0, record at +256
 constexpr size_t XCHG_BYTES = 2 * XCHG_SLOT;
+// The exchange arena of a rank (one cudaMalloc, mapped by its peers through CUDA IPC):
+//   [0, XCHG_BYTES)            two record slots (above)
+//   XCHG_BYTES                 u32: this rank's "a peer timed out" flag (local use)
+//   XCHG_BYTES + 64            u64: epoch of the evaluation vector below (release/acquire at system scope)
+//   XCHG_BYTES + 256 ...       eval_cap field elements: this rank's transformed vector of the split witness map
+constexpr size_t EVAL_FLAG_OFF = XCHG_BYTES + 64;
+constexpr size_t EVAL_OFF = XCHG_BYTES + 256;
+constexpr int MAP_RANKS = 3;                          // a, b, c are transformed on ranks 0, 1, 2
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;
@@ -299,6 +308,43 @@ __global__ void xchg_gather_kernel(uint8_t* const* __restrict__ peers, int count
         asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + threadIdx.x) : "memory");
         reinterpret_cast<uint4*>(gathered + (size_t)k * REC_BYTES)[threadIdx.x] = v;
     }
+}
+
+// Split witness map (sharded proofs on >= 3 GPUs).  Rank k < 3 transforms ONE of a, b, c (natural-order evaluations on H ->
+// evaluations on the coset, qap.rs:60-72) into its arena and releases the epoch; every rank then forms its own slice of
+// h = a*b - c (qap.rs:75-85) reading the three vectors straight out of peer HBM over NVLink: the transform work is divided by
+// three, and the exchange is fused into the pointwise kernel (no collective, no host round trip).
+__global__ void eval_publish_kernel(uint8_t* __restrict__ arena, const unsigned long long* __restrict__ epoch_ctr) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(arena + EVAL_FLAG_OFF), *epoch_ctr + 1ull);
+    }
+}
+
+__device__ __forceinline__ fe fe_load_sys(const void* p) {
+    fe r;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]) : "l"((const char*)p + 16) : "memory");
+    return r;
+}
+
+__global__ void __launch_bounds__(256) h_slice_kernel(uint8_t* const* __restrict__ peers, const unsigned long long* __restrict__ epoch_ctr, uint32_t lo, uint32_t cnt,
+                                                      fe* __restrict__ h, unsigned long long timeout_ns, unsigned int* __restrict__ timed_out) {
+    const unsigned long long epoch = *epoch_ctr + 1ull;
+    if (threadIdx.x < MAP_RANKS) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(peers[threadIdx.x] + EVAL_FLAG_OFF);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(flag) < epoch) {
+            if (global_timer_ns() - t0 > timeout_ns) { atomicExch(timed_out, 1u + threadIdx.x); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const size_t off = EVAL_OFF + (size_t)(lo + i) * sizeof(fe);
+    const fe a = fe_load_sys(peers[0] + off), b = fe_load_sys(peers[1] + off), c = fe_load_sys(peers[2] + off);
+    fe_store(&h[lo + i], Fr::sub(Fr::mul(a, b), c));
 }
 
 // ------------------------------------------------------------------------------------------------ small utility kernels
@@ -496,7 +542,37 @@ static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
 static const int WITNESS_ORDER[4] = {Q_B2, Q_A, Q_B1, Q_L};     // the G2 MSM is the longest: start it first
 
 // scale: also compute s*msm_A and r*msm_B1 (d_rs must hold r, s) on those MSMs' own streams, right behind them
-static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed, bool scale) {
+static unsigned long long p2p_timeout_ns() {
+    const char* v = getenv("B2G_P2P_TIMEOUT_MS");
+    long ms = v && *v ? strtol(v, nullptr, 10) : 20000;
+    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+}
+
+static bool map_is_split(const b2g_ctx* ctx, const b2g_mat* mat) {
+    return ctx->shard_count >= MAP_RANKS && ctx->peers_imported == ctx->shard_count && mat->reduction == B2G_REDUCTION_CIRCOM &&
+           ctx->eval_common >= mat->n && getenv("B2G_NO_SPLIT_MAP") == nullptr;
+}
+
+// witness map of a sharded proof with the three transforms on ranks 0, 1, 2 (kernels above); fills d_h[lo, lo + cnt) only
+static void run_witness_map_split(b2g_ctx* ctx, b2g_mat* mat, uint32_t lo, uint32_t cnt, cudaStream_t st) {
+    const int rank = ctx->shard_rank;
+    unsigned int* d_flag = reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES);
+    if (rank < MAP_RANKS) {
+        fe* eval = reinterpret_cast<fe*>(ctx->d_xchg + EVAL_OFF);
+        spmv_launch(mat->n, mat->m, mat->num_inputs, mat->a_rowptr, mat->a_col, mat->a_val, mat->b_rowptr, mat->b_col, mat->b_val, ctx->d_w,
+                    rank == 0 ? eval : ctx->d_a, rank == 1 ? eval : ctx->d_b, rank == 2 ? eval : ctx->d_c, st);
+        ntt_transform_single(mat->dom, eval, st);
+        eval_publish_kernel<<<1, 32, 0, st>>>(ctx->d_xchg, ctx->d_epoch);
+        g_launch_count += 1;
+    }
+    if (cnt) {
+        h_slice_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(ctx->d_peer_ptrs, ctx->d_epoch, lo, cnt, ctx->d_h, p2p_timeout_ns(), d_flag);
+        g_launch_count += 1;
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed, bool scale, bool split_map = false) {
     cudaStream_t s0 = ctx->st[0], ssort = ctx->st[Q_L];
     CUDA_CHECK(cudaEventRecord(ctx->ev_w, s0));
     CUDA_CHECK(cudaStreamWaitEvent(ssort, ctx->ev_w, 0));
@@ -515,7 +591,8 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed, bool
         CUDA_CHECK(cudaEventRecord(ctx->ev_done[q], ctx->st[q]));
     }
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[10], s0));
-    run_witness_map(ctx, mat, s0);
+    if (split_map) run_witness_map_split(ctx, mat, pk->lo[Q_H], pk->cnt[Q_H], s0);
+    else run_witness_map(ctx, mat, s0);
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[11], s0));
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[0], s0));
     msm_run(pk->plan[Q_H], ctx->scratch[Q_H], ctx->d_h + pk->lo[Q_H], pk->cnt[Q_H], true, s0);   // pairs min(#bases, #h) terms
@@ -563,23 +640,18 @@ static void launch_glue_post(b2g_ctx* ctx, b2g_pk* pk, const uint8_t* partials_d
     CUDA_CHECK(cudaGetLastError());
 }
 
-static unsigned long long p2p_timeout_ns() {
-    const char* v = getenv("B2G_P2P_TIMEOUT_MS");
-    long ms = v && *v ? strtol(v, nullptr, 10) : 20000;
-    return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
-}
 
 // Everything one proof does on the device between "witness and (r, s) are in HBM" and "proof bytes are in d_proof".
 // kind 0: whole proof; kind 1: base-sharded proof whose partials are exchanged through NVLink peer memory.
 static void enqueue_proof(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int kind, bool timed) {
     cudaStream_t s0 = ctx->st[0];
+    unsigned int* d_flag = kind == 1 ? reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES) : nullptr;   // local word after the two slots
+    if (kind == 1) CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 4, s0));
     launch_glue_pre(ctx, pk);
-    launch_msms(ctx, pk, mat, timed, true);
+    launch_msms(ctx, pk, mat, timed, true, kind == 1 && map_is_split(ctx, mat));
     if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[14], s0));
     if (kind == 1) {
         xchg_publish_kernel<<<1, 64, 0, s0>>>(ctx->d_partial, ctx->d_xchg, ctx->d_epoch);
-        unsigned int* d_flag = reinterpret_cast<unsigned int*>(ctx->d_xchg + XCHG_BYTES);       // local word after the two slots
-        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 4, s0));
         xchg_gather_kernel<<<ctx->shard_count, 64, 0, s0>>>(ctx->d_peer_ptrs, ctx->shard_count, ctx->d_epoch, ctx->d_partials_all, p2p_timeout_ns(), d_flag);
         g_launch_count += 2;
         launch_glue_post(ctx, pk, ctx->d_partials_all, ctx->shard_count, true, s0);
@@ -653,12 +725,27 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         DevGuard g(device);
         b2g_ctx* ctx = new b2g_ctx();
         ctx->device = device; ctx->shard_rank = shard_rank; ctx->shard_count = shard_count;
-        for (int i = 0; i < NQ; i++) { CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st[i], cudaStreamNonBlocking)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
+        // Several contexts on one GPU = several proofs in flight.  With equal priorities they advance in lock step (all sorting,
+        // then all accumulating ...) and leave each other's latency-bound phases uncovered; giving successive contexts of a
+        // device descending stream priorities turns them into a pipeline: the oldest context's proof runs at full speed and the
+        // others fill its gaps.  (The MSM tail kernels keep the highest priority on every context.)  B2G_CTX_PRIORITY_SPREAD=0: off.
+        int prio = 0;
+        {
+            static std::atomic<unsigned> ctx_seq[64];
+            int least = 0, greatest = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            const char* sp = getenv("B2G_CTX_PRIORITY_SPREAD");
+            const int levels = least - greatest - 1;                        // levels below the tail kernels' priority
+            if (!(sp && *sp == '0') && levels >= 2 && shard_count == 1) prio = greatest + 1 + (int)(ctx_seq[device & 63]++ % (unsigned)(levels < 3 ? levels : 3));
+            else prio = least;
+        }
+        ctx->stream_priority = prio;
+        for (int i = 0; i < NQ; i++) { CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->st[i], cudaStreamNonBlocking, prio)); CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); }
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_w, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sort, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->st_glue, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->st_glue, cudaStreamNonBlocking, prio));
         for (auto& e : ctx->ev_t) CUDA_CHECK(cudaEventCreate(&e));
         CUDA_CHECK(cudaMalloc(&ctx->d_partial, REC_BYTES));
         CUDA_CHECK(cudaMemset(ctx->d_partial, 0, REC_BYTES));
@@ -673,8 +760,6 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         { const char* g = getenv("B2G_GRAPH"); ctx->use_graph = !(g && *g == '0'); }
         // tuning knob: L2 -> DRAM fetch granularity hint (bytes: 32 / 64 / 128) for the 64-byte table gathers (profiles/r2_load_width.md)
         { const char* g = getenv("B2G_L2_FETCH"); if (g && *g) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)strtol(g, nullptr, 10)); cudaGetLastError(); }
-        CUDA_CHECK(cudaMalloc(&ctx->d_xchg, XCHG_BYTES + 256));            // plain cudaMalloc: exportable through CUDA IPC
-        CUDA_CHECK(cudaMemset(ctx->d_xchg, 0, XCHG_BYTES + 256));
         CUDA_CHECK(cudaMalloc(&ctx->d_peer_ptrs, 64 * sizeof(uint8_t*)));
         msm_init_kernels();
         *out = ctx;
@@ -971,14 +1056,30 @@ int b2g_ctx_prepare(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
     });
 }
 
+}  // extern "C"
+// the arena is sized for the largest domain this context has been prepared for (b2g_ctx_prepare / a first proof): call that
+// BEFORE wiring the peers, or the witness map stays replicated on every rank
+static void ensure_arena(b2g_ctx* ctx) {
+    if (ctx->d_xchg) return;
+    ctx->eval_cap = ctx->cap_n;
+    const size_t bytes = EVAL_OFF + ctx->eval_cap * sizeof(fe);
+    CUDA_CHECK(cudaMalloc(&ctx->d_xchg, bytes));                       // plain cudaMalloc: exportable through CUDA IPC
+    CUDA_CHECK(cudaMemset(ctx->d_xchg, 0, EVAL_OFF));
+}
+extern "C" {
+
 int b2g_p2p_export(b2g_ctx* ctx, void* handle_out) {
     return guarded([&] {
         if (!ctx || !handle_out) throw_error(B2G_E_SHAPE, "null pointer");
-        static_assert(sizeof(cudaIpcMemHandle_t) == B2G_IPC_HANDLE_BYTES, "IPC handle size");
+        static_assert(sizeof(cudaIpcMemHandle_t) + 16 == B2G_IPC_HANDLE_BYTES, "IPC handle size");
         DevGuard g(ctx->device);
+        ensure_arena(ctx);
         cudaIpcMemHandle_t h;
         CUDA_CHECK(cudaIpcGetMemHandle(&h, ctx->d_xchg));
+        memset(handle_out, 0, B2G_IPC_HANDLE_BYTES);
         memcpy(handle_out, &h, sizeof h);
+        const uint64_t cap = ctx->eval_cap;
+        memcpy((uint8_t*)handle_out + sizeof h, &cap, 8);
     });
 }
 
@@ -987,16 +1088,24 @@ int b2g_p2p_import(b2g_ctx* ctx, const void* handles_all, int count) {
         if (!ctx || !handles_all) throw_error(B2G_E_SHAPE, "null pointer");
         if (count != ctx->shard_count) throw_error(B2G_E_SHAPE, "need one handle per shard rank");
         DevGuard g(ctx->device);
+        ensure_arena(ctx);
         std::vector<uint8_t*> ptrs((size_t)count, nullptr);
+        uint64_t common = ctx->eval_cap;
+        for (int k = 0; k < count; k++) {
+            const uint8_t* rec = (const uint8_t*)handles_all + (size_t)k * B2G_IPC_HANDLE_BYTES;
+            uint64_t cap = 0; memcpy(&cap, rec + sizeof(cudaIpcMemHandle_t), 8);
+            if (k != ctx->shard_rank && cap < common) common = cap;
+        }
+        ctx->eval_common = (size_t)common;
         for (int k = 0; k < count; k++) {
             if (k == ctx->shard_rank) { ptrs[k] = ctx->d_xchg; continue; }
-            cudaIpcMemHandle_t h; memcpy(&h, (const uint8_t*)handles_all + (size_t)k * sizeof h, sizeof h);
+            cudaIpcMemHandle_t h; memcpy(&h, (const uint8_t*)handles_all + (size_t)k * B2G_IPC_HANDLE_BYTES, sizeof h);
             void* p = nullptr;
             CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
             ctx->peer_mapped[k] = p; ptrs[k] = (uint8_t*)p;
         }
         CUDA_CHECK(cudaMemcpy(ctx->d_peer_ptrs, ptrs.data(), (size_t)count * sizeof(uint8_t*), cudaMemcpyHostToDevice));
-        ctx->peers_imported = count;
+        ctx->peers_imported = count; ctx->alloc_gen++;          // captured graphs were built without the peers
     });
 }
 
@@ -1005,7 +1114,9 @@ int b2g_p2p_connect_local(b2g_ctx** ctxs, int count) {
         if (!ctxs || count < 1 || count > 64) throw_error(B2G_E_SHAPE, "bad arguments");
         for (int k = 0; k < count; k++) if (!ctxs[k] || ctxs[k]->shard_rank != k || ctxs[k]->shard_count != count) throw_error(B2G_E_SHAPE, "contexts must be the shard ranks 0..count-1 in order");
         std::vector<uint8_t*> ptrs((size_t)count);
-        for (int k = 0; k < count; k++) ptrs[k] = ctxs[k]->d_xchg;
+        size_t common = (size_t)-1;
+        for (int k = 0; k < count; k++) { DevGuard g(ctxs[k]->device); ensure_arena(ctxs[k]); ptrs[k] = ctxs[k]->d_xchg; common = std::min(common, ctxs[k]->eval_cap); }
+        for (int k = 0; k < count; k++) ctxs[k]->eval_common = common;
         for (int k = 0; k < count; k++) {
             DevGuard g(ctxs[k]->device);
             for (int j = 0; j < count; j++) if (ctxs[j]->device != ctxs[k]->device) {
@@ -1014,7 +1125,7 @@ int b2g_p2p_connect_local(b2g_ctx** ctxs, int count) {
                 cudaGetLastError();
             }
             CUDA_CHECK(cudaMemcpy(ctxs[k]->d_peer_ptrs, ptrs.data(), (size_t)count * sizeof(uint8_t*), cudaMemcpyHostToDevice));
-            ctxs[k]->peers_imported = count;
+            ctxs[k]->peers_imported = count; ctxs[k]->alloc_gen++;
         }
     });
 }

@@ -103,7 +103,7 @@ class Context:
         N.check(N.lib().b2g_ctx_prepare(self._h, self.pk_handle(pk), self.mat_handle(matrices, pk.n_vars, reduction_id)))
 
     def p2p_export(self) -> bytes:
-        buf = np.zeros(64, dtype=np.uint8)
+        buf = np.zeros(N.IPC_HANDLE_BYTES, dtype=np.uint8)
         N.check(N.lib().b2g_p2p_export(self._h, _ptr(buf)))
         return buf.tobytes()
 

@@ -45,8 +45,9 @@ def prove_sharded(ctx, pk, matrices, w_mont, r, s, dist, device=None, group=None
 
 
 def connect_p2p(ctx, dist, group=None) -> None:
-    """Exchange the CUDA-IPC handles of every rank's exchange buffer (host-side, once) so that Groth16.prove_sharded_p2p
-    can fold the partials straight out of NVLink peer memory."""
+    """Exchange the CUDA-IPC handles of every rank's exchange arena (host-side, once) so that Groth16.prove_sharded_p2p
+    can fold the partials - and, with >= 3 ranks, read the three transformed vectors of the split witness map - straight out
+    of NVLink peer memory.  Call ctx.prepare(pk, matrices) first: the arena is sized for the prepared domain."""
     handles = [None] * dist.get_world_size()
     dist.all_gather_object(handles, ctx.p2p_export(), group=group)
     ctx.p2p_import(handles)

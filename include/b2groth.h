@@ -146,9 +146,13 @@ B2G_API int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all,
  * through CUDA IPC.  b2g_prove_sharded_p2p runs the partial MSMs, publishes the partial with a system-scope release of
  * the epoch, and the assembly kernel acquires every peer's epoch and folds the partials straight out of peer memory in
  * rank order.  All ranks must call it for the same proof; every rank obtains identical bytes.
- *   b2g_p2p_export  : 64-byte cudaIpcMemHandle_t of this context's exchange buffer
- *   b2g_p2p_import  : handles of ALL ranks in rank order (count x 64 bytes; the own entry is ignored) */
-#define B2G_IPC_HANDLE_BYTES 64
+ *   b2g_p2p_export  : B2G_IPC_HANDLE_BYTES: the cudaIpcMemHandle_t of this context's exchange arena + its capacity
+ *   b2g_p2p_import  : records of ALL ranks in rank order (count x B2G_IPC_HANDLE_BYTES; the own entry is ignored)
+ * With >= 3 ranks the witness map is split as well (CircomReduction): ranks 0, 1, 2 each transform ONE of a, b, c into their
+ * arena, and every rank forms its slice of h = a*b - c reading the three vectors from peer HBM inside the pointwise kernel.
+ * The arena is sized when it is first needed (export / import / connect_local) for the largest domain the context has been
+ * prepared for, so call b2g_ctx_prepare BEFORE wiring the peers; otherwise every rank computes the whole map itself. */
+#define B2G_IPC_HANDLE_BYTES 80
 B2G_API int b2g_p2p_export(b2g_ctx* ctx, void* handle_out);
 B2G_API int b2g_p2p_import(b2g_ctx* ctx, const void* handles_all, int count);
 /* same wiring for shard contexts that live in ONE process (IPC handles cannot be opened by their exporter): ctxs in rank order */

@@ -616,8 +616,8 @@ def _p2p_worker(rank, world, port, q):
         wm = fr_to_mont(pyref.chain_witness(pk.n_vars, g['a']))
         dev = rank % torch.cuda.device_count()
         ctx = Context(dev, rank, world)
+        ctx.prepare(pk, cm)                                      # before the wiring: the exchange arena is sized for this domain
         sharding.connect_p2p(ctx, dist)                          # CUDA-IPC handles over gloo
-        ctx.prepare(pk, cm)
         dist.barrier()
         ok = True
         for _ in range(3):                                       # several epochs: both exchange slots are reused
@@ -632,19 +632,21 @@ def _p2p_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_sharded_proof_fused_peer_memory_exchange():
-    """b2g_prove_sharded_p2p, one process per shard (two GPUs if present, else both on GPU 0): each rank publishes its
-    partial MSM results with a system-scope release and folds its peers' partials straight out of their HBM (CUDA IPC
-    mapping) inside the kernels; both ranks must produce the golden proof."""
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_proof_fused_peer_memory_exchange(world):
+    """b2g_prove_sharded_p2p, one process per shard (one GPU each if the box has them, else all on GPU 0): each rank publishes
+    its partial MSM results with a system-scope release and folds its peers' partials straight out of their HBM (CUDA IPC
+    mapping) inside the captured proof graph; every rank must produce the golden proof.  world = 4 also runs the SPLIT
+    witness map: a, b, c transformed on ranks 0, 1, 2, every rank forming its slice of h = a*b - c from peer memory."""
     import torch.multiprocessing as mp
     mpc = mp.get_context('spawn')
     q = mpc.Queue()
-    port = 29600 + (os.getpid() % 300)
-    procs = [mpc.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 300) + world
+    procs = [mpc.Process(target=_p2p_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in procs]
-    res = sorted(q.get(timeout=150) for _ in range(2))
+    res = sorted(q.get(timeout=240) for _ in range(world))
     [p.join(timeout=30) for p in procs]
-    assert res == [(0, True), (1, True)], res
+    assert res == [(r, True) for r in range(world)], res
 
 
 def test_off_curve_key_point_is_rejected(ctx, test_zkey_bytes):
