@@ -46,6 +46,8 @@ struct b2g_ctx {
     uint8_t* d_proof = nullptr;          // 256 B
     uint8_t* d_pre = nullptr;            // glue precomputation: r*d1, s*d1, rs*d1, K_C (G1 XYZZ) + s*d2 (G2 XYZZ)
     fe *d_w = nullptr, *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
+    fe* d_wb = nullptr; size_t cap_wb = 0;     // gathered scalars of a sparse B query (b2g_pk::d_bidx)
+    cudaEvent_t ev_sortb = nullptr; bool scratch_bsort = false;
     size_t cap_w = 0, cap_n = 0;
     float last_ms[16] = {};
     bool pre_valid = false; uint32_t pre_r[8] = {}, pre_s[8] = {};   // (r, s) whose glue_pre result sits in d_pre
@@ -78,6 +80,11 @@ struct b2g_pk {
     uint8_t* d_consts = nullptr;         // G1: alpha, beta, delta, a_query[0], b_g1_query[0] (5 x 64) ; G2: beta, delta, b_g2_query[0] (3 x 128)
     void *d_tab_delta1 = nullptr, *d_tab_delta2 = nullptr;   // 8-bit window tables of delta_g1 / delta_g2 (32 x 255 affine points)
     void *d_tab_aa = nullptr, *d_tab_bb = nullptr;           // same for alpha_g1 + a_query[0] and beta_g1 + b_g1_query[0] (glue_pre: K_C)
+    // Sparse B: real circom keys have b_g1/b_g2_query entries at infinity for every wire that never occurs in a B row.  When
+    // fewer than 80 % of this shard's B bases are real points, B1 and B2 are built over the compacted set only: d_bidx[j] =
+    // position (inside the shard's w[1..] range) of the j-th real base; the proof gathers those scalars and sorts them on their own
+    uint32_t* d_bidx = nullptr;
+    uint32_t b_compact = 0;
 };
 
 struct b2g_mat {
@@ -347,6 +354,11 @@ __global__ void __launch_bounds__(256) h_slice_kernel(uint8_t* const* __restrict
     fe_store(&h[lo + i], Fr::sub(Fr::mul(a, b), c));
 }
 
+__global__ void __launch_bounds__(256) gather_scalars_kernel(const fe* __restrict__ w, const uint32_t* __restrict__ idx, uint32_t n, fe* __restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) fe_store(&out[j], fe_load_nc(&w[idx[j]]));
+}
+
 // ------------------------------------------------------------------------------------------------ small utility kernels
 template <class C, class F>
 __global__ void xyzz_to_affine_kernel(const void* __restrict__ pts, uint32_t n, void* __restrict__ out) {
@@ -488,7 +500,7 @@ static void ensure_witness_buffers(b2g_ctx* ctx, size_t n_vars, size_t n) {
 
 // per-stream MSM scratch of this context, sized for `pk` (re-created if a later key is larger)
 static void ensure_scratch(b2g_ctx* ctx, const b2g_pk* pk) {
-    bool ok = ctx->scratch_ok;
+    bool ok = ctx->scratch_ok && (!pk->d_bidx || (ctx->scratch_bsort && pk->b_compact <= ctx->cap_wb));
     for (int q = 0; q < NQ && ok; q++) {
         const MsmPlan& p = pk->plan[q]; const MsmScratch& sc = ctx->scratch[q];
         if ((p.n ? p.n : 1) > sc.cap_n || p.nwin > sc.cap_nwin || p.nbuckets > sc.cap_buckets) ok = false;
@@ -498,10 +510,16 @@ static void ensure_scratch(b2g_ctx* ctx, const b2g_pk* pk) {
     if (ctx->scratch_ok) { for (int q = 0; q < NQ; q++) msm_scratch_free(ctx->scratch[q]); ctx->scratch_ok = false; }
     for (int q = 0; q < NQ; q++) {
         const MsmPlan& p = pk->plan[q];
-        msm_scratch_alloc(ctx->scratch[q], p.n ? p.n : 1, p.nwin, p.nbuckets, q == Q_B2, q == Q_H || q == Q_L);
+        msm_scratch_alloc(ctx->scratch[q], p.n ? p.n : 1, p.nwin, p.nbuckets, q == Q_B2, q == Q_H || q == Q_L || (q == Q_B1 && pk->d_bidx));
         cudaFree(ctx->scratch[q].result);
         ctx->scratch[q].result = ctx->d_partial + PARTIAL_OFF[q];
         ctx->scratch[q].result_owned = false;
+    }
+    ctx->scratch_bsort = pk->d_bidx != nullptr;
+    if (pk->b_compact > ctx->cap_wb) {
+        if (ctx->d_wb) cudaFree(ctx->d_wb);
+        CUDA_CHECK(cudaMalloc(&ctx->d_wb, ((size_t)pk->b_compact + 1) * sizeof(fe)));
+        ctx->cap_wb = pk->b_compact;
     }
     ctx->scratch_ok = true; ctx->alloc_gen++;
 }
@@ -578,10 +596,22 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed, bool
     CUDA_CHECK(cudaStreamWaitEvent(ssort, ctx->ev_w, 0));
     msm_sort(pk->plan[Q_A], ctx->scratch[Q_L], ctx->d_w + pk->scalar_off[Q_A] + pk->lo[Q_A], pk->cnt[Q_A], true, ssort);
     CUDA_CHECK(cudaEventRecord(ctx->ev_sort, ssort));
+    const bool bsparse = pk->d_bidx != nullptr;
+    if (bsparse) {
+        // B1 and B2 over the compacted base set: gather their scalars and sort them separately (on the B1 stream)
+        cudaStream_t sb = ctx->st[Q_B1];
+        CUDA_CHECK(cudaStreamWaitEvent(sb, ctx->ev_w, 0));
+        if (pk->b_compact) gather_scalars_kernel<<<(pk->b_compact + 255) / 256, 256, 0, sb>>>(ctx->d_w + pk->scalar_off[Q_B1] + pk->lo[Q_B1], pk->d_bidx, pk->b_compact, ctx->d_wb);
+        g_launch_count += 1;
+        msm_sort(pk->plan[Q_B1], ctx->scratch[Q_B1], ctx->d_wb, pk->b_compact, true, sb);
+        CUDA_CHECK(cudaEventRecord(ctx->ev_sortb, sb));
+    }
     for (int q : WITNESS_ORDER) {
-        if (q != Q_L) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sort, 0));
+        const bool on_b = bsparse && (q == Q_B1 || q == Q_B2);
+        if (on_b) { if (q != Q_B1) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sortb, 0)); }
+        else if (q != Q_L) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sort, 0));
         if (timed) CUDA_CHECK(cudaEventRecord(ctx->ev_t[2 * q], ctx->st[q]));
-        msm_accumulate(pk->plan[q], ctx->scratch[Q_L], ctx->scratch[q], ctx->st[q]);
+        msm_accumulate(pk->plan[q], on_b ? ctx->scratch[Q_B1] : ctx->scratch[Q_L], ctx->scratch[q], ctx->st[q]);
         if (scale && (q == Q_A || q == Q_B1)) {
             const Scalar256* rs = reinterpret_cast<const Scalar256*>(ctx->d_rs);
             scale_partial_kernel<<<1, 32, 0, ctx->st[q]>>>(ctx->d_partial + PARTIAL_OFF[q], q == Q_A ? rs + 1 : rs, ctx->d_partial + B2G_PARTIAL_BYTES + (q == Q_A ? 0 : 128));
@@ -608,6 +638,7 @@ static void pk_release(b2g_pk* pk) {
     if (pk->d_tab_delta2) cudaFree(pk->d_tab_delta2);
     if (pk->d_tab_aa) cudaFree(pk->d_tab_aa);
     if (pk->d_tab_bb) cudaFree(pk->d_tab_bb);
+    if (pk->d_bidx) cudaFree(pk->d_bidx);
     delete pk;
 }
 
@@ -745,6 +776,7 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sort, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_pre, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_sortb, cudaEventDisableTiming));
         CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->st_glue, cudaStreamNonBlocking, prio));
         for (auto& e : ctx->ev_t) CUDA_CHECK(cudaEventCreate(&e));
         CUDA_CHECK(cudaMalloc(&ctx->d_partial, REC_BYTES));
@@ -772,7 +804,8 @@ int b2g_ctx_destroy(b2g_ctx* ctx) {
         DevGuard g(ctx->device);
         cudaDeviceSynchronize();
         for (int i = 0; i < NQ; i++) { if (ctx->scratch_ok) msm_scratch_free(ctx->scratch[i]); cudaStreamDestroy(ctx->st[i]); cudaEventDestroy(ctx->ev_done[i]); }
-        cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_fork); cudaStreamDestroy(ctx->st_glue);
+        cudaEventDestroy(ctx->ev_w); cudaEventDestroy(ctx->ev_sort); cudaEventDestroy(ctx->ev_pre); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_sortb); cudaStreamDestroy(ctx->st_glue);
+        if (ctx->d_wb) cudaFree(ctx->d_wb);
         for (auto& g : ctx->gexec) if (g) cudaGraphExecDestroy(g);
         if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
         if (ctx->h_proof) cudaFreeHost(ctx->h_proof);
@@ -812,6 +845,8 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
         const uint32_t base_skip[NQ] = {0, 0, 1, 1, 1};             // query[0] is added separately for A/B1/B2
         const uint32_t soff[NQ] = {0, 1, 1, 1, 1};                  // first scalar: h[0] / w[1]
         const void* src[NQ] = {d->h_query, l_padded.data(), d->a_query, d->b_g1_query, d->b_g2_query};
+        std::vector<uint32_t> bidx;                                   // real (non-infinity) B bases of this shard, see b2g_pk::d_bidx
+        std::vector<uint8_t> bpacked[2];
         for (int q = 0; q < NQ; q++) {
             const bool g2 = q == Q_B2;
             const size_t aff = g2 ? 128 : 64;
@@ -820,6 +855,28 @@ int b2g_pk_load(b2g_ctx* ctx, const b2g_pk_desc* d, b2g_pk** out) {
             pk->cnt[q] = (uint32_t)((uint64_t)total[q] * (r + 1) / R) - pk->lo[q];
             pk->scalar_off[q] = soff[q];
             if (total[q] && !src[q]) throw_error(B2G_E_SHAPE, "null proving-key section");
+            if (q == Q_B1) {
+                // support of the B polynomials inside this shard: a base counts if it is a real point in either group
+                const uint8_t* b1 = (const uint8_t*)d->b_g1_query + (size_t)(1 + pk->lo[q]) * 64;
+                const uint8_t* b2 = (const uint8_t*)d->b_g2_query + (size_t)(1 + pk->lo[q]) * 128;
+                auto nonzero = [](const uint8_t* p, size_t n) { const uint64_t* w = (const uint64_t*)p; uint64_t o = 0; for (size_t i = 0; i < n / 8; i++) o |= w[i]; return o != 0; };
+                for (uint32_t i = 0; i < pk->cnt[q]; i++) if (nonzero(b1 + (size_t)i * 64, 64) || nonzero(b2 + (size_t)i * 128, 128)) bidx.push_back(i);
+                const char* off = getenv("B2G_NO_B_COMPACT");
+                if (!(off && *off == '1') && pk->cnt[q] >= 1024 && (uint64_t)bidx.size() * 5 < (uint64_t)pk->cnt[q] * 4) {
+                    pk->b_compact = (uint32_t)bidx.size();
+                    bpacked[0].resize(bidx.size() * 64 + 64); bpacked[1].resize(bidx.size() * 128 + 128);
+                    for (size_t j = 0; j < bidx.size(); j++) { memcpy(&bpacked[0][j * 64], b1 + (size_t)bidx[j] * 64, 64); memcpy(&bpacked[1][j * 128], b2 + (size_t)bidx[j] * 128, 128); }
+                    pk->d_bidx = dev_upload<uint32_t>(bidx.data(), bidx.size() * 4, st);
+                } else bidx.clear();
+            }
+            if (pk->d_bidx && (q == Q_B1 || q == Q_B2)) {
+                if (pk->b_compact) guard.tmp = dev_upload<uint8_t>(bpacked[g2 ? 1 : 0].data(), (size_t)pk->b_compact * aff, st);
+                msm_build_table(pk->plan[q], guard.tmp, pk->b_compact, g2, st);
+                g_launch_count += 1;
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                if (guard.tmp) { cudaFree(guard.tmp); guard.tmp = nullptr; }
+                continue;
+            }
             if (pk->cnt[q]) guard.tmp = dev_upload<uint8_t>((const uint8_t*)src[q] + (size_t)(base_skip[q] + pk->lo[q]) * aff, (size_t)pk->cnt[q] * aff, st);
             msm_build_table(pk->plan[q], guard.tmp, pk->cnt[q], g2, st);
             g_launch_count += 1;
@@ -1182,14 +1239,16 @@ int b2g_bench_msm(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int query, int iters, 
         DevGuard g(ctx->device);
         cudaStream_t s0 = ctx->st[0];
         MsmScratch& sc = ctx->scratch[query];
-        MsmScratch& sorter = ctx->scratch[query == Q_H ? Q_H : Q_L];
-        const fe* scalars = (query == Q_H ? ctx->d_h : ctx->d_w + pk->scalar_off[query]) + pk->lo[query];
+        const bool on_b = pk->d_bidx && (query == Q_B1 || query == Q_B2);      // sparse B: compacted scalars of the last proof
+        MsmScratch& sorter = ctx->scratch[query == Q_H ? Q_H : (on_b ? Q_B1 : Q_L)];
+        const fe* scalars = on_b ? ctx->d_wb : (query == Q_H ? ctx->d_h : ctx->d_w + pk->scalar_off[query]) + pk->lo[query];
+        const uint32_t nscal = on_b ? pk->b_compact : pk->cnt[query];
         std::vector<cudaEvent_t> ev(2 * (size_t)iters);
         for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[18], s0));
         for (int it = 0; it < iters; it++) {
             sc.prof0 = ev[2 * it]; sc.prof1 = ev[2 * it + 1];
-            msm_sort(pk->plan[query], sorter, scalars, pk->cnt[query], true, s0);
+            msm_sort(pk->plan[query], sorter, scalars, nscal, true, s0);
             msm_accumulate(pk->plan[query], sorter, sc, s0);
         }
         sc.prof0 = sc.prof1 = nullptr;

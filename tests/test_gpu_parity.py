@@ -665,6 +665,33 @@ def test_off_curve_key_point_is_rejected(ctx, test_zkey_bytes):
     release(cm)
 
 
+def test_load_time_validation(ctx, test_zkey_bytes, monkeypatch):
+    """What b2g_pk_load / b2g_matrices_load refuse: off-curve alpha / delta / query[0] (the reference's G1Affine::new and
+    G2Affine::new validate every point, src/zkey.rs:340-360), malformed CSR row pointers
+    and an out-of-range window override."""
+    from circom_compat_b200 import read_zkey, B2gError, ConstraintMatrices
+    for field, idx in (('alpha_g1', (0, 1)), ('delta_g1', (0, 0)), ('delta_g2', (0, 3)), ('a_query', (0, 2)), ('b_g2_query', (0, 9)), ('beta_g2', (0, 0))):
+        pk, _ = read_zkey(test_zkey_bytes)
+        arr = getattr(pk, field).copy(); arr[idx] ^= 2; setattr(pk, field, arr)
+        if field in ('a_query', 'b_g2_query') and not arr[0].any():
+            continue                                              # query[0] at infinity in this key: nothing to corrupt
+        with pytest.raises(B2gError) as e:
+            ctx.pk_handle(pk)
+        assert e.value.code == -4 and 'not on the curve' in str(e.value), field
+    from circom_compat_b200 import synth
+    cm = synth.chain_circuit(8).matrices()                        # 6 rows, one entry each: rowptr = 0..6
+    for rowptr in ([1, 1, 2, 3, 4, 5, 6], [0, 2, 1, 3, 4, 5, 6]):
+        bad = ConstraintMatrices(cm.num_instance_variables, cm.num_witness_variables, cm.num_constraints, cm.a_num_non_zero, cm.b_num_non_zero, 0,
+                                 (np.array(rowptr, dtype=np.uint32), cm.a[1], cm.a[2]), cm.b)
+        with pytest.raises(B2gError) as e:
+            ctx.mat_handle(bad, 8)
+        assert e.value.code == -2 and 'row' in str(e.value), rowptr
+    monkeypatch.setenv('B2G_MSM_C', '5')
+    with pytest.raises(B2gError) as e:
+        ctx.msm_g1(c.fixed_base_g1(c.ints_to_limbs([1, 2, 3])), c.ints_to_limbs([1, 2, 3]))
+    assert e.value.code == -2 and 'B2G_MSM_C' in str(e.value)
+
+
 # ------------------------------------------------------------------------------------------------ edge cases
 def _prove_both(ctx, circ, w, r, s, td_seed=7):
     """GPU proof and CPU-oracle proof on a fresh synthetic key; returns (gpu bytes, oracle bytes, pk, td)"""
