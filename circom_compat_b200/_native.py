@@ -36,7 +36,7 @@ class MatDesc(C.Structure):
 
 
 EXPORTS = ['b2g_last_error', 'b2g_version', 'b2g_device_count', 'b2g_ctx_create', 'b2g_ctx_destroy', 'b2g_ctx_prepare', 'b2g_pk_load', 'b2g_pk_free',
-           'b2g_matrices_load', 'b2g_matrices_free', 'b2g_witness_map', 'b2g_prove', 'b2g_prove_submit', 'b2g_prove_wait', 'b2g_prove_partial', 'b2g_prove_finish',
+           'b2g_matrices_load', 'b2g_matrices_free', 'b2g_witness_map', 'b2g_prove', 'b2g_prove_submit', 'b2g_prove_wait', 'b2g_host_register', 'b2g_host_unregister', 'b2g_prove_partial', 'b2g_prove_finish',
            'b2g_p2p_export', 'b2g_p2p_import', 'b2g_p2p_connect_local', 'b2g_prove_sharded_p2p', 'b2g_msm_g1', 'b2g_msm_g2', 'b2g_ntt', 'b2g_fixed_base_g1', 'b2g_fixed_base_g2', 'b2g_test_op', 'b2g_last_timings',
            'b2g_bench_device', 'b2g_bench_msm', 'b2g_launch_count']
 
@@ -66,6 +66,8 @@ def lib():
         L.b2g_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_prove_submit.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_prove_wait.argtypes = [vp]
+        L.b2g_host_register.argtypes = [vp, sz]
+        L.b2g_host_unregister.argtypes = [vp]
         L.b2g_prove_partial.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.b2g_prove_finish.argtypes = [vp, vp, vp, i, vp, vp, vp]
         L.b2g_p2p_export.argtypes = [vp, vp]

@@ -1061,6 +1061,24 @@ int b2g_prove_submit(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon
     });
 }
 
+int b2g_host_register(const void* ptr, size_t bytes) {
+    return guarded([&] {
+        if (!ptr || !bytes) throw_error(B2G_E_SHAPE, "null pointer");
+        cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+        if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) CUDA_CHECK(e);
+        cudaGetLastError();
+    });
+}
+
+int b2g_host_unregister(const void* ptr) {
+    return guarded([&] {
+        if (!ptr) throw_error(B2G_E_SHAPE, "null pointer");
+        cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+        if (e != cudaSuccess && e != cudaErrorHostMemoryNotRegistered) CUDA_CHECK(e);
+        cudaGetLastError();
+    });
+}
+
 int b2g_prove_wait(b2g_ctx* ctx) {
     return guarded([&] {
         if (!ctx) throw_error(B2G_E_SHAPE, "null pointer");

@@ -380,6 +380,43 @@ struct Groth16T {                                       // Groth16::<Bn254, QAP>
         return p;
     }
 
+    // Many proofs for one key, `inflight` of them queued on the GPU at any time, driven by THIS thread alone
+    // (b2g_prove_submit / b2g_prove_wait on `inflight` contexts): what a rayon pool around the synchronous call does in the
+    // reference's world.  rs[i] = (r, s) and assignments[i] = full assignment of proof i; witnesses are page-locked for the
+    // duration of the call so that their upload overlaps the previous proofs.  Proofs are returned in order.
+    static std::vector<Proof> prove_batch(const ProvingKey& pk, const ConstraintMatrices& matrices, const std::vector<std::pair<Fr, Fr>>& rs,
+                                          const std::vector<const std::vector<Fr>*>& assignments, int inflight = 3, int device = 0) {
+        if (rs.size() != assignments.size()) throw SynthesisError("prove_batch: one (r, s) per assignment");
+        const size_t n = rs.size();
+        if (inflight < 1) inflight = 1;
+        std::vector<std::unique_ptr<Gpu>> gpus;
+        for (int k = 0; k < inflight && (size_t)k < n; k++) gpus.emplace_back(new Gpu(device));
+        std::vector<Proof> out(n);
+        std::vector<BigInt256> rb(n), sb(n);
+        for (size_t i = 0; i < n; i++) {
+            if (assignments[i]->size() != pk.a_query.size()) throw SynthesisError("AssignmentMissing: full_assignment length != n_vars");
+            rb[i] = rs[i].first.into_bigint(); sb[i] = rs[i].second.into_bigint();
+            check(b2g_host_register(assignments[i]->data(), assignments[i]->size() * sizeof(Fr)));
+        }
+        auto submit = [&](size_t i) {
+            Gpu& g = *gpus[i % gpus.size()];
+            check(b2g_prove_submit(g.ctx(), g.pk(pk), g.mat(matrices, assignments[i]->size(), QAP::ID), rb[i].l, sb[i].l, assignments[i]->data(), out[i].bytes));
+        };
+        size_t submitted = 0;
+        try {
+            for (; submitted < gpus.size(); submitted++) submit(submitted);
+            for (size_t done = 0; done < n; done++) {
+                check(b2g_prove_wait(gpus[done % gpus.size()]->ctx()));
+                if (submitted < n) submit(submitted++);
+            }
+        } catch (...) {
+            for (size_t i = 0; i < n; i++) b2g_host_unregister(assignments[i]->data());
+            throw;
+        }
+        for (size_t i = 0; i < n; i++) b2g_host_unregister(assignments[i]->data());
+        return out;
+    }
+
     template <class Rng>
     static Proof prove(const ProvingKey& pk, const ConstraintMatrices& matrices, const std::vector<Fr>& full_assignment, Rng& rng,
                        Gpu& gpu = Gpu::instance()) {

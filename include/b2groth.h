@@ -129,6 +129,11 @@ B2G_API int b2g_prove(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_cano
 B2G_API int b2g_prove_submit(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_canon, const void* s_canon, const void* w_mont,
                              uint8_t proof_out[256]);
 B2G_API int b2g_prove_wait(b2g_ctx* ctx);
+/* Page-lock / release a host buffer (cudaHostRegister): a witness vector owned by the caller (a Rust Vec<Fr>, a std::vector)
+ * uploads asynchronously and at full PCIe speed once registered.  Registering twice / unregistering an unknown pointer is not
+ * an error. */
+B2G_API int b2g_host_register(const void* ptr, size_t bytes);
+B2G_API int b2g_host_unregister(const void* ptr);
 
 /* Sharded proof.  partial_out (768 B, host or device-accessible host memory) = this rank's partial MSM results
  * [H, L, A, B1] as G1 XYZZ (128 B each) followed by B2 as G2 XYZZ (256 B), mont.  b2g_prove_finish folds

@@ -403,8 +403,9 @@ def test_cpp_host_mirror_proves_golden(golden, tmp_path):
     exe = os.path.join(root, 'circom_compat_b200', 'host', 'groth16_bench')
     g = golden['complex_zkey']
     out = subprocess.check_output([exe, os.path.join(root, 'tests', 'golden', 'complex-circuit-10000-10000.zkey'), 'chain:%d' % g['a'], '2',
-                                   '%x' % int(g['r']), '%x' % int(g['s'])], text=True)
+                                   '%x' % int(g['r']), '%x' % int(g['s'])], text=True, env=dict(os.environ, B2G_INFLIGHT='3'))
     assert 'proof=' + g['proof_hex'] in out and 'verified=1' in out      # C++ process_vk + verify_with_processed_vk
+    assert 'pipelined (3 in flight' in out and 'identical=1' in out      # Groth16::prove_batch: submit / wait on three contexts
     gt = golden['test_zkey']
     w = [int(x) for x in gt['witness']]
     wt = tmp_path / 'w.wtns'
