@@ -756,10 +756,10 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         DevGuard g(device);
         b2g_ctx* ctx = new b2g_ctx();
         ctx->device = device; ctx->shard_rank = shard_rank; ctx->shard_count = shard_count;
-        // Several contexts on one GPU = several proofs in flight.  With equal priorities they advance in lock step (all sorting,
-        // then all accumulating ...) and leave each other's latency-bound phases uncovered; giving successive contexts of a
-        // device descending stream priorities turns them into a pipeline: the oldest context's proof runs at full speed and the
-        // others fill its gaps.  (The MSM tail kernels keep the highest priority on every context.)  B2G_CTX_PRIORITY_SPREAD=0: off.
+        // Stream priority of this context's proof streams (the MSM tail kernels always run at the highest).  Measured on B200
+        // (gpurun_out/r2_b6_*.json): spreading successive contexts over different priorities to pipeline concurrent proofs was
+        // NOT better than equal priorities (48 vs 55-57 proofs/s device-resident, e2e unchanged), so it is opt-in:
+        // B2G_CTX_PRIORITY_SPREAD=1.
         int prio = 0;
         {
             static std::atomic<unsigned> ctx_seq[64];
@@ -767,7 +767,7 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
             CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
             const char* sp = getenv("B2G_CTX_PRIORITY_SPREAD");
             const int levels = least - greatest - 1;                        // levels below the tail kernels' priority
-            if (!(sp && *sp == '0') && levels >= 2 && shard_count == 1) prio = greatest + 1 + (int)(ctx_seq[device & 63]++ % (unsigned)(levels < 3 ? levels : 3));
+            if (sp && *sp == '1' && levels >= 2 && shard_count == 1) prio = greatest + 1 + (int)(ctx_seq[device & 63]++ % (unsigned)(levels < 3 ? levels : 3));
             else prio = least;
         }
         ctx->stream_priority = prio;
@@ -790,8 +790,11 @@ int b2g_ctx_create(int device, int shard_rank, int shard_count, b2g_ctx** out) {
         CUDA_CHECK(cudaMalloc(&ctx->d_epoch, 8));
         CUDA_CHECK(cudaMemset(ctx->d_epoch, 0, 8));
         { const char* g = getenv("B2G_GRAPH"); ctx->use_graph = !(g && *g == '0'); }
-        // tuning knob: L2 -> DRAM fetch granularity hint (bytes: 32 / 64 / 128) for the 64-byte table gathers (profiles/r2_load_width.md)
-        { const char* g = getenv("B2G_L2_FETCH"); if (g && *g) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)strtol(g, nullptr, 10)); cudaGetLastError(); }
+        // L2 -> DRAM fetch granularity: the device default (128 B) makes every 64-byte gather from the fixed-base tables cost 128 B
+        // of DRAM; 64 B halves the traffic of the G1 accumulation (2.04 -> 1.08 GB per 2^20 launch, ncu) at unchanged speed
+        // (profiles/r2_load_width.md).  Device-wide hint; B2G_L2_FETCH=128 restores the default, 32 / 64 / 128 accepted.
+        { const char* g = getenv("B2G_L2_FETCH"); const size_t gran = g && *g ? (size_t)strtol(g, nullptr, 10) : 64;
+          if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); cudaGetLastError(); }
         CUDA_CHECK(cudaMalloc(&ctx->d_peer_ptrs, 64 * sizeof(uint8_t*)));
         msm_init_kernels();
         *out = ctx;
