@@ -412,12 +412,12 @@ def run_ours(args):
                 "algorithmic_bytes": alg, "kernel_ms": acc_ms, "whole_msm_ms": msm_ms,
                 "traffic_source": "static: " + prof.get("source", "no committed ncu summary (profiles/kernel_profile.json missing)"),
                 "note": "254-bit Pippenger is bound by the IMAD.WIDE (fmaheavy) pipe, not by HBM (DESIGN.md section 5)"}
-        if prof.get("g1_imad_wide_per_launch") and args.log_n == prof.get("log_n") and shard_div == 1:
-            peak_int = 148 * 4 * 32 / 4 * 1.965e9           # 148 SMs x 4 sub-partitions x 32 lanes, one IMAD.WIDE per 4 cycles, 1.965 GHz
-            ach_int = prof["g1_imad_wide_per_launch"] / (acc_ms * 1e-3)
-            roof["int_pipe"] = {"bound": "IMAD.WIDE issue (fmaheavy pipe)", "achieved": ach_int / 1e12, "peak": peak_int / 1e12, "unit": "T IMAD.WIDE/s",
-                                "frac": ach_int / peak_int, "imad_wide_per_launch": prof["g1_imad_wide_per_launch"],
-                                "source": "static thread-level IMAD.WIDE count of the kernel group (" + prof.get("source", "") + ") / live CUDA-event time"}
+        if prof.get("g1_fmaheavy_pct") and args.log_n == prof.get("log_n") and shard_div == 1:
+            # the binding roofline: the integer multiply-add ("fmaheavy") pipe.  Utilisation is a static ncu fact of the kernel
+            # (sm__pipe_fmaheavy_cycles_active), rescaled by ncu-time / live CUDA-event time of this run
+            frac = prof["g1_fmaheavy_pct"] / 100.0 * (prof["g1_time_us_ncu"] * 1e-3) / acc_ms
+            roof["int_pipe"] = {"bound": "IMAD.WIDE issue (fmaheavy pipe)", "frac": frac, "static_pct_ncu": prof["g1_fmaheavy_pct"],
+                                "static_kernel_us_ncu": prof["g1_time_us_ncu"], "source": "static: " + prof.get("source", "")}
         g2_ms, g2_acc = ctx.bench_msm(pk, cm, 4, 3)
         extra["msm_g2"] = {"whole_msm_ms": g2_ms, "kernel_ms": g2_acc, "algorithmic_gbs": (pk.n_vars - 1) / shard_div * 160.0 / (g2_acc * 1e-3) / 1e9}
         extra["single_proof_latency_ms"] = main["latency_ms"]

@@ -1001,7 +1001,7 @@ int b2g_witness_map(b2g_ctx* ctx, b2g_mat* mat, const void* w_mont, void* h_out,
     });
 }
 
-static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont) {
+static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_mont, bool slice_only = false) {
     check_shapes(ctx, pk, mat);
     if (!w_mont) throw_error(B2G_E_SHAPE, "null witness");
     ensure_witness_buffers(ctx, mat->n_vars, mat->n);
@@ -1009,7 +1009,11 @@ static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_m
     cudaStream_t s0 = ctx->st[0];
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[12], s0));
     static const bool skip_upload = getenv("B2G_DEBUG_NO_H2D") != nullptr;      // diagnosis only: reuse the resident witness
-    if (!skip_upload || ctx->debug_uploaded != mat->uid) CUDA_CHECK(cudaMemcpyAsync(ctx->d_w, w_mont, (size_t)mat->n_vars * 32, cudaMemcpyHostToDevice, s0));
+    // a rank that takes no part in the split witness map needs only the scalars of its own base range
+    size_t first = 0, count = mat->n_vars;
+    if (slice_only && map_is_split(ctx, mat) && ctx->shard_rank >= MAP_RANKS) { first = (size_t)pk->scalar_off[Q_A] + pk->lo[Q_A]; count = pk->cnt[Q_A]; }
+    if ((!skip_upload || ctx->debug_uploaded != mat->uid) && count)
+        CUDA_CHECK(cudaMemcpyAsync(ctx->d_w + first, (const uint8_t*)w_mont + first * 32, count * 32, cudaMemcpyHostToDevice, s0));
     ctx->debug_uploaded = mat->uid;
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[13], s0));
 }
@@ -1217,7 +1221,7 @@ int b2g_prove_sharded_p2p(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_
         if (ctx->peers_imported != ctx->shard_count) throw_error(B2G_E_SHAPE, "b2g_p2p_import has not been called with every rank's handle");
         DevGuard g(ctx->device);
         check_shapes(ctx, pk, mat);
-        prove_common(ctx, pk, mat, w_mont);
+        prove_common(ctx, pk, mat, w_mont, true);
         stage_rs(ctx, r_canon, s_canon);
         cudaStream_t s0 = ctx->st[0];
         run_proof(ctx, pk, mat, 1);
