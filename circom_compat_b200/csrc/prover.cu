@@ -1239,7 +1239,9 @@ int b2g_prove_sharded_p2p(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* r_
 
 int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* avg_ms) {
     return guarded([&] {
-        if (!avg_ms || iters < 1) throw_error(B2G_E_SHAPE, "bad arguments");
+        if (!avg_ms || iters == 0) throw_error(B2G_E_SHAPE, "bad arguments");
+        const bool no_wait = iters < 0;                                   // enqueue only: the caller synchronises and times the window
+        if (no_wait) iters = -iters;
         check_shapes(ctx, pk, mat);
         if (ctx->cap_w < mat->n_vars) throw_error(B2G_E_SHAPE, "no witness resident: call b2g_prove first");
         DevGuard g(ctx->device);
@@ -1253,6 +1255,7 @@ int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* a
         for (int it = 0; it < iters; it++) run_proof(ctx, pk, mat, 0);
         ctx->pre_valid = false;
         CUDA_CHECK(cudaEventRecord(ctx->ev_t[17], s0));
+        if (no_wait) { *avg_ms = 0.f; return; }
         CUDA_CHECK(cudaStreamSynchronize(s0));
         float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t[16], ctx->ev_t[17]));
         *avg_ms = ms / iters;

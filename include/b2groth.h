@@ -188,7 +188,9 @@ B2G_API int b2g_test_op(b2g_ctx* ctx, int op, const void* a, const void* b, size
 B2G_API int b2g_last_timings(b2g_ctx* ctx, float out_ms[16]);
 
 /* Benchmark helper: the device-resident part of a proof (witness already in HBM from the last b2g_prove call):
- * runs witness map + 5 MSMs + glue `iters` times and returns the average CUDA-event milliseconds. */
+ * runs witness map + 5 MSMs + glue `iters` times and returns the average CUDA-event milliseconds.  iters < 0: enqueue
+ * |iters| proofs and return without waiting (*avg_ms = 0): the caller synchronises the device and times the window itself,
+ * which is how several contexts are measured over ONE common window. */
 B2G_API int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, float* avg_ms);
 /* One MSM alone on the main stream, `iters` times (query: 0 H, 1 L, 2 A, 3 B1, 4 B2): out_ms[0] = average CUDA-event
  * milliseconds of the whole MSM, out_ms[1] = of its bucket-accumulation kernel (the dominant kernel, for the roofline). */
