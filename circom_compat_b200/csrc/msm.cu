@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(128) msm_aff_apply_kernel(const void* __restri
 // occupancy targets: G1 runs 4 CTAs/SM at 126 registers; G2 sits at 174 registers, 1 % over the 3-CTA limit (170), so it
 // is capped there (ncu: 2 CTAs/SM left the IMAD pipe waiting on dependent-issue latency with 2 warps per scheduler)
 template <class F> struct AccOcc;
-template <> struct AccOcc<Fq> { static constexpr int MIN_CTAS = 4; };
+#ifndef B2G_G1_CTAS
+#define B2G_G1_CTAS 4
+#endif
+template <> struct AccOcc<Fq> { static constexpr int MIN_CTAS = B2G_G1_CTAS; };
 #ifndef B2G_G2_CTAS
 #define B2G_G2_CTAS 3
 #endif

@@ -96,6 +96,13 @@ def test_synthetic_setup_is_a_valid_groth16_key(kind, tmp_path):
     assert o.verify(z, w[1:circ.num_inputs], proof)
     da, db, dc = synth.expected_proof_dlogs(td, w, fr_from_mont(h), r, s, circ.num_inputs)
     assert o.G1.mul(o.G1_GEN, da) == proof[0] and o.G2.mul(o.G2_GEN, db) == proof[1] and o.G1.mul(o.G1_GEN, dc) == proof[2]
+    # the h-free closed form (H term = (a(tau) b(tau) - c(tau)) / delta from the matrix rows): same discrete logs, and it
+    # moves when the witness breaks a constraint while the h-based form follows whatever h it is given
+    assert synth.expected_proof_dlogs_independent(td, circ, w, r, s) == (da, db, dc)
+    wbad = list(w); wbad[5] = (wbad[5] + 1) % o.R_MOD
+    hbad = fr_from_mont(c.witness_map(circ.num_constraints, circ.num_inputs, circ.n_vars, circ.matrices().a, circ.matrices().b, fr_to_mont(wbad)))
+    assert synth.expected_proof_dlogs_independent(td, circ, wbad, r, s) == synth.expected_proof_dlogs(td, wbad, hbad, r, s, circ.num_inputs)
+    assert synth.expected_proof_dlogs_independent(td, circ, wbad, r, s) != synth.expected_proof_dlogs(td, wbad, fr_from_mont(h), r, s, circ.num_inputs)
     pk2, cm2 = read_zkey(data)
     assert pk2.n_vars == circ.n_vars and cm2.num_constraints == circ.num_constraints
 
