@@ -61,20 +61,13 @@ __device__ __forceinline__ fe fe_load(const void* p) {
     fe r; r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
 }
-// read-only (non-coherent) load of one element.  Default: two 128-bit LDG.CONSTANT; -DB2G_LD256: one 256-bit
-// ld.global.nc.v8.u32 (LDG.E.ENL2.256.CONSTANT on sm_100a) - measured in profiles/r2_load_width.md
+// read-only (non-coherent) load of one element: two 128-bit LDG.CONSTANT.  (One 256-bit ld.global.nc.v8.u32 =
+// LDG.E.ENL2.256.CONSTANT was measured in round 2: no difference on these pipe-bound kernels, profiles/r2_load_width.md.)
 __device__ __forceinline__ fe fe_load_nc(const void* p) {
-#ifdef B2G_LD256
-    fe r;
-    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]) : "l"(p));
-    return r;
-#else
     const uint4* q = reinterpret_cast<const uint4*>(p);
     uint4 a = __ldg(q), b = __ldg(q + 1);
     fe r; r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
     return r;
-#endif
 }
 __device__ __forceinline__ void fe_store(void* p, const fe& v) {
     uint4* q = reinterpret_cast<uint4*>(p);

@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(128) msm_aff_apply_kernel(const void* __restri
 // Thread t owns sorted positions [t*chunk, (t+1)*chunk).  Buckets that lie entirely inside the run are written to
 // buckets[]; a run's first / last segment that belongs to a bucket crossing the run boundary goes to frag_first[t] /
 // frag_last[t].
-// occupancy targets: G1 runs 4 CTAs/SM at 126 registers; G2 sits at 174 registers, 1 % over the 3-CTA limit (170), so it
+// occupancy targets (measured, round 2: 5 / 6 CTAs per SM for G1 = 96 / 80 registers: 2.343 / 2.410 ms vs 2.361 ms; register caps
+// of 120 / 160 that leave room for a co-resident sort CTA: e2e 49.3 vs 50.3 proofs/s - neither kept): G1 runs 4 CTAs/SM at 126 registers; G2 sits at 174 registers, 1 % over the 3-CTA limit (170), so it
 // is capped there (ncu: 2 CTAs/SM left the IMAD pipe waiting on dependent-issue latency with 2 warps per scheduler)
 template <class F> struct AccOcc;
 #ifndef B2G_G1_CTAS
@@ -338,18 +339,8 @@ template <> struct AccOcc<Fq> { static constexpr int MIN_CTAS = B2G_G1_CTAS; };
 #endif
 template <> struct AccOcc<Fq2> { static constexpr int MIN_CTAS = B2G_G2_CTAS; };
 
-// -DB2G_ACC_REGCAP: cap the registers instead (G1 120, G2 160: 4 / 3 CTAs of 128 threads then leave 4096 registers per SM
-// free, room for one small CTA of a pipe-light kernel - the digit sort of the next proof - next to the accumulation)
-#ifdef B2G_ACC_REGCAP
-template <class F> struct AccRegs;
-template <> struct AccRegs<Fq> { static constexpr int N = 120; };
-template <> struct AccRegs<Fq2> { static constexpr int N = 160; };
-#define B2G_ACC_ATTR(F) __maxnreg__(AccRegs<F>::N)
-#else
-#define B2G_ACC_ATTR(F) __launch_bounds__(128, AccOcc<F>::MIN_CTAS)
-#endif
 template <class C, class F>
-__global__ void B2G_ACC_ATTR(F) msm_accumulate_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
+__global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
                                       const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
                                       void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last) {
     using Pt = typename C::Pt; using Aff = typename C::Aff;
@@ -623,15 +614,7 @@ void msm_sort(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_
     if (n == 0 || plan.table == nullptr) return;
     if (n > s.cap_n || plan.nwin > s.cap_nwin || plan.nbuckets > s.cap_buckets || !s.entries) throw_error(B2G_E_SHAPE, "msm: sort scratch too small");
     const uint32_t nb = plan.nbuckets;
-#ifdef B2G_ACC_REGCAP
-    // the sort is pipe-light (L2 atomics): as 128-thread CTAs of <= 32 registers on the high-priority stream it slips into the
-    // 4096 registers per SM the capped accumulation kernels leave free and runs NEXT TO the accumulation of the proofs in flight
-    constexpr unsigned SORT_CTA = 128;
-    cudaStream_t main_st = st;
-    if (s.tail) { CUDA_CHECK(cudaEventRecord(s.ev_acc, st)); CUDA_CHECK(cudaStreamWaitEvent(s.tail, s.ev_acc, 0)); st = s.tail; }
-#else
     constexpr unsigned SORT_CTA = 256;
-#endif
     CUDA_CHECK(cudaMemsetAsync(s.counts, 0, (size_t)nb * 4, st));
     const unsigned pair_blocks = (unsigned)(((uint64_t)n * plan.nwin + SORT_CTA - 1) / SORT_CTA);
     msm_canon_kernel<<<(n + SORT_CTA - 1) / SORT_CTA, SORT_CTA, 0, st>>>(scalars_dev, n, scalars_mont ? 1 : 0, s.scalars_canon);
@@ -639,9 +622,6 @@ void msm_sort(const MsmPlan& plan, MsmScratch& s, const fe* scalars_dev, uint32_
     msm_scan_kernel<<<1, 1024, 0, st>>>(s.counts, nb, s.offsets, s.cursor);
     // table rows are indexed w * plan.n + i (the table was built over plan.n bases, n may be shorter)
     msm_scatter_kernel<<<pair_blocks, SORT_CTA, 0, st>>>(s.scalars_canon, n, plan.n, plan.c, plan.nwin, s.offsets, s.cursor, s.entries);
-#ifdef B2G_ACC_REGCAP
-    if (s.tail) { CUDA_CHECK(cudaEventRecord(s.ev_tail, s.tail)); CUDA_CHECK(cudaStreamWaitEvent(main_st, s.ev_tail, 0)); st = main_st; }
-#endif
     g_launch_count += 4;
     // level structure of the batched-affine pre-reduction (shared by every query accumulated against this sort)
     s.aff_rounds = s.aff_off_dev ? s.aff_cap_rounds : 0;

@@ -6,7 +6,6 @@ run() { # name, env...
   env "$@" B2G_GRAPH=0 ncu --metrics $M --clock-control none -k regex:msm_accumulate -c 12 --csv --log-file gpurun_out/r2_lw_$name.csv python tools/prof_msm.py 20 1 > gpurun_out/r2_lw_$name.log 2>&1
 }
 run base X=1
-run ld256 B2G_LIB=$PWD/circom_compat_b200/libb2groth_ld256.so
 run fetch32 B2G_L2_FETCH=32
 run fetch64 B2G_L2_FETCH=64
 run fetch128 B2G_L2_FETCH=128
