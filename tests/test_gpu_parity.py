@@ -356,6 +356,62 @@ def test_submit_wait_pipelines_proofs_on_one_thread(golden, complex_zkey_bytes):
         cx.close()
 
 
+def test_graph_and_direct_launch_paths_agree(golden, complex_zkey_bytes, monkeypatch):
+    """The captured proof graph (default) and direct launches (B2G_GRAPH=0 at context creation) are the same pipeline: same
+    golden bytes; a context switches keys (re-capture on a new key uid) and comes back."""
+    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, Context
+    pk, cm = read_zkey(complex_zkey_bytes)
+    g = golden['complex_zkey']
+    wm = fr_to_mont(o.chain_witness(pk.n_vars, g['a']))
+    monkeypatch.setenv('B2G_GRAPH', '0')
+    direct = Context(0)
+    monkeypatch.delenv('B2G_GRAPH')
+    graph = Context(0)
+    for cx in (direct, graph, graph, direct):
+        p = Groth16.create_proof_with_reduction_and_matrices(pk, int(g['r']), int(g['s']), cm, cm.num_instance_variables, cm.num_constraints, wm, cx)
+        assert p.data.hex() == g['proof_hex']
+    t = direct.last_timings()
+    assert t['witness_map'] > 0 and t['msm_b2'] > 0                  # interior phase timers exist only without the graph
+    assert graph.last_timings()['msm_b2'] == 0 and graph.last_timings()['total'] > 0
+    # another key on the same contexts, then the first one again
+    from circom_compat_b200 import synth
+    circ = synth.chain_circuit(1 << 10); w2 = synth.chain_witness(1 << 10)
+    pk2, td = synth.setup(graph, circ); cm2 = circ.matrices()
+    p2 = Groth16.create_proof_with_reduction_and_matrices(pk2, 3, 4, cm2, circ.num_inputs, circ.num_constraints, fr_to_mont(w2), graph)
+    assert p2.data == c.prove(_oracle_key(pk2, cm2), 3, 4, fr_to_mont(w2))
+    p = Groth16.create_proof_with_reduction_and_matrices(pk, int(g['r']), int(g['s']), cm, cm.num_instance_variables, cm.num_constraints, wm, graph)
+    assert p.data.hex() == g['proof_hex']
+    direct.close(); graph.close()
+
+
+def test_sparse_b_compaction_matches_uncompacted(ctx, monkeypatch):
+    """Keys whose B query is mostly points at infinity (real circom keys; here the circom-like circuit: B touches 768 of ~9 000
+    wires) are proved over the compacted B bases with their own scalar sort; same bytes as with compaction disabled and as the
+    CPU oracle, also when the shard ranges cut the key in three."""
+    from circom_compat_b200 import Groth16, fr_to_mont, synth, release, Context
+    circ, w = synth.circomlike_circuit(13)
+    pk, td = synth.setup(ctx, circ)
+    nb = int(np.count_nonzero(np.asarray(pk.b_g1_query).reshape(pk.n_vars, -1).any(axis=1)))
+    assert nb * 5 < pk.n_vars                                          # sparse enough for the compacted path
+    cm = circ.matrices()
+    wm = fr_to_mont(w)
+    r, s = 0xabcdef0123, 0x456789
+    ref = c.prove(_oracle_key(pk, cm), r, s, wm)
+    p1 = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    parts, ctxs = [], []
+    for rank in range(3):
+        cx = Context(0, rank, 3); ctxs.append(cx)
+        parts.append(Groth16.prove_partial(pk, cm, wm, cx))
+    p3 = Groth16.prove_finish(pk, np.stack(parts), r, s, ctxs[0])
+    release(pk)
+    monkeypatch.setenv('B2G_NO_B_COMPACT', '1')
+    p2 = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    assert p1.data == ref and p2.data == ref and p3.data == ref
+    release(pk); release(cm)
+    for cx in ctxs:
+        cx.close()
+
+
 def test_sharded_proof_equals_whole_proof(golden, complex_zkey_bytes):
     # base-range sharding on one device: 3 shard contexts, partials folded in rank order
     from circom_compat_b200 import read_zkey, Groth16, fr_to_mont, Context
