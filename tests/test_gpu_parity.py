@@ -372,7 +372,7 @@ def test_graph_and_direct_launch_paths_agree(golden, complex_zkey_bytes, monkeyp
         assert p.data.hex() == g['proof_hex']
     t = direct.last_timings()
     assert t['witness_map'] > 0 and t['msm_b2'] > 0                  # interior phase timers exist only without the graph
-    assert graph.last_timings()['msm_b2'] == 0 and graph.last_timings()['total'] > 0
+    assert graph.last_timings()['msm_b2'] < 0.05 < graph.last_timings()['total']     # no interior events inside the graph
     # another key on the same contexts, then the first one again
     from circom_compat_b200 import synth
     circ = synth.chain_circuit(1 << 10); w2 = synth.chain_witness(1 << 10)
