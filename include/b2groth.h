@@ -147,10 +147,12 @@ B2G_API int b2g_prove_finish(b2g_ctx* ctx, b2g_pk* pk, const void* partials_all,
                      const void* s_canon, uint8_t proof_out[256]);
 
 /* Sharded proof with the exchange fused into the proof-assembly kernel (NVLink peer memory instead of a host-driven
- * collective).  Every rank owns an exchange buffer in its HBM (two slots of 768 B + an epoch word each); peers map it
- * through CUDA IPC.  b2g_prove_sharded_p2p runs the partial MSMs, publishes the partial with a system-scope release of
- * the epoch, and the assembly kernel acquires every peer's epoch and folds the partials straight out of peer memory in
- * rank order.  All ranks must call it for the same proof; every rank obtains identical bytes.
+ * collective).  Every rank owns an exchange arena in its HBM (two slots of a 1 KiB record - the 768-byte partial plus s*A_k and
+ * r*B1_k - with an epoch word each, then room for one transformed vector of the split witness map); peers map it through CUDA
+ * IPC.  b2g_prove_sharded_p2p runs the partial MSMs, publishes the record with a system-scope release of the epoch, and the
+ * gather kernel acquires every peer's epoch and reads the records straight out of peer memory; the assembly folds them in rank
+ * order.  The whole sharded proof, exchange included, is one captured CUDA graph (the epoch is a device-resident counter).
+ * All ranks must call it for the same proof; every rank obtains identical bytes.
  *   b2g_p2p_export  : B2G_IPC_HANDLE_BYTES: the cudaIpcMemHandle_t of this context's exchange arena + its capacity
  *   b2g_p2p_import  : records of ALL ranks in rank order (count x B2G_IPC_HANDLE_BYTES; the own entry is ignored)
  * With >= 3 ranks the witness map is split as well (CircomReduction): ranks 0, 1, 2 each transform ONE of a, b, c into their
@@ -195,7 +197,8 @@ B2G_API int b2g_bench_device(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int iters, 
 /* One MSM alone on the main stream, `iters` times (query: 0 H, 1 L, 2 A, 3 B1, 4 B2): out_ms[0] = average CUDA-event
  * milliseconds of the whole MSM, out_ms[1] = of its bucket-accumulation kernel (the dominant kernel, for the roofline). */
 B2G_API int b2g_bench_msm(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, int query, int iters, float out_ms[2]);
-/* number of kernel launches issued by this library on the ctx since creation */
+/* number of kernel launches issued by this library (process-wide, all contexts) so far; a replayed proof graph counts the kernel
+ * nodes it contains */
 B2G_API int b2g_launch_count(b2g_ctx* ctx, uint64_t* count);
 
 #ifdef __cplusplus
