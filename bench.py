@@ -348,9 +348,8 @@ def run_ours(args):
             per = [steps // inflight + (1 if i < steps % inflight else 0) for i in range(inflight)]
             barrier()
             t0 = time.perf_counter()
-            for i in range(inflight):
-                if per[i]:
-                    ctxs[i].bench_device(pk, cm, -per[i])                 # enqueue only (one graph launch per proof), no wait
+            for k in range(steps):                                        # round-robin over the contexts, like the e2e loop
+                ctxs[k % inflight].bench_device(pk, cm, -1)               # enqueue only (one graph launch per proof), no wait
             torch.cuda.synchronize()
             dev_local = time.perf_counter() - t0
             dev_s = max_over_ranks(dev_local)
