@@ -342,11 +342,37 @@ template <> struct AccOcc<Fq2> { static constexpr int MIN_CTAS = B2G_G2_CTAS; };
 template <class C, class F>
 __global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kernel(const void* __restrict__ table, const uint32_t* __restrict__ entries,
                                       const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
-                                      void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last) {
+                                      void* __restrict__ buckets, void* __restrict__ frag_first, void* __restrict__ frag_last, uint32_t slab_words) {
     using Pt = typename C::Pt; using Aff = typename C::Aff;
     const uint32_t total = offsets[nb];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t start64 = (uint64_t)t * chunk;
+    // slab_words != 0 (default for G1): the CTA's contiguous slab of the sorted entry list (128 runs = 32 KB at the default run
+    // length) is brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk -> UBLKCP, completion on an mbarrier)
+    // instead of 64 strided 4-byte loads per thread
+    extern __shared__ __align__(128) uint32_t slab[];
+    __shared__ __align__(8) unsigned long long slab_bar;
+    const uint64_t cta_first = (uint64_t)blockIdx.x * blockDim.x * chunk;
+    if (slab_words) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&slab_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && cta_first < total) {
+            const uint64_t left = total - cta_first;
+            const uint32_t bytes = (uint32_t)(((left < slab_words ? left : (uint64_t)slab_words) * 4 + 15) & ~15ull);    // the list is padded by 16 B
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(slab)), "l"(entries + cta_first), "r"(bytes), "r"(bar) : "memory");
+        }
+        if (cta_first < total) {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+        }
+    }
     if (start64 >= total) return;
     const uint32_t start = (uint32_t)start64;
     const uint32_t end = (uint32_t)min((uint64_t)total, start64 + chunk);
@@ -359,7 +385,7 @@ __global__ void __launch_bounds__(128, AccOcc<F>::MIN_CTAS) msm_accumulate_kerne
     Pt acc = C::infinity();
     uint32_t seg_start = start;
     for (uint32_t pos = start; pos < end;) {
-        const uint32_t e = entries ? entries[pos] : pos;      // entries == nullptr: `table` is a pre-reduced point list (4a)
+        const uint32_t e = slab_words ? slab[pos - (uint32_t)cta_first] : (entries ? entries[pos] : pos);   // entries == nullptr: `table` is a pre-reduced point list (4a)
         Aff p = aff_load<F>(table, (size_t)(e & 0x7fffffffu));
         if (e >> 31) p.y = F::neg(p.y);
         C::madd(acc, p);
@@ -397,17 +423,39 @@ __global__ void __launch_bounds__(128) msm_fold_kernel(const uint32_t* __restric
     pt_store<F>(buckets, b, acc);
 }
 
-// shared-memory tree sum of one point per thread; result valid in thread 0
+// sum of one point per thread; result valid in thread 0.  Inside a warp the partial sums travel by register shuffles
+// (lane i adds lane i + d, d = 16 .. 1: the classic butterfly, every limb of the XYZZ point through __shfl_down_sync); the one
+// or two warp results are then combined through shared memory.
+template <class F> struct PtWords;
+template <> struct PtWords<Fq> { static constexpr int N = 32; };
+template <> struct PtWords<Fq2> { static constexpr int N = 64; };
+
+template <class C, class F>
+__device__ __forceinline__ typename C::Pt warp_sum_points(typename C::Pt v) {
+    using Pt = typename C::Pt;
+    static_assert(sizeof(Pt) == PtWords<F>::N * 4, "XYZZ point layout");
+    #pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+        Pt q;
+        uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+        const uint32_t* vw = reinterpret_cast<const uint32_t*>(&v);
+        #pragma unroll
+        for (int i = 0; i < PtWords<F>::N; i++) qw[i] = __shfl_down_sync(0xffffffffu, vw[i], d);
+        if ((int)(threadIdx.x & 31) < d) C::add(v, q);
+    }
+    return v;
+}
+
 template <class C, class F, int NT>
 __device__ __forceinline__ typename C::Pt block_sum_points(typename C::Pt v, typename C::Pt* sh) {
-    sh[threadIdx.x] = v;
+    static_assert(NT == 32 || NT == 64, "one or two warps");
+    v = warp_sum_points<C, F>(v);
+    if (NT == 32) return v;
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
-    #pragma unroll 1
-    for (int d = NT / 2; d > 0; d >>= 1) {
-        if ((int)threadIdx.x < d) { typename C::Pt a = sh[threadIdx.x]; typename C::Pt q = sh[threadIdx.x + d]; C::add(a, q); sh[threadIdx.x] = a; }
-        __syncthreads();
-    }
-    return sh[0];
+    if (threadIdx.x == 0) { typename C::Pt q = sh[1]; C::add(v, q); }
+    __syncthreads();                                       // sh may be reused by the caller's next round
+    return v;
 }
 
 // Tail kernels (fold_big / reduce / sum) are latency chains on a few CTAs.  Their CTAs are kept smaller than one
@@ -544,7 +592,7 @@ void msm_scratch_alloc(MsmScratch& s, uint32_t n, int nwin, uint32_t nbuckets, b
         CUDA_CHECK(cudaMalloc(&s.counts, (size_t)nbuckets * 4));
         CUDA_CHECK(cudaMalloc(&s.offsets, ((size_t)nbuckets + 1) * 4));
         CUDA_CHECK(cudaMalloc(&s.cursor, (size_t)nbuckets * 4));
-        CUDA_CHECK(cudaMalloc(&s.entries, (nent + 1) * 4));
+        CUDA_CHECK(cudaMalloc(&s.entries, (nent + 8) * 4));          // + 16 B: the bulk copy of the last slab is rounded up
         CUDA_CHECK(cudaMalloc(&s.scalars_canon, ((size_t)n + 1) * sizeof(fe)));
     }
     CUDA_CHECK(cudaMalloc(&s.big_list, (size_t)nbuckets * 4));
@@ -673,9 +721,17 @@ static void msm_accumulate_t(const MsmPlan& plan, const MsmScratch& sorted, MsmS
         g_launch_count += 3 * rounds;
         offsets = sorted.aff_off[rounds];
         const uint32_t nthreads_r = (uint32_t)(((uint64_t)sorted.aff_nmax[rounds] + chunk - 1) / chunk);
-        msm_accumulate_kernel<C, F><<<(nthreads_r + 127) / 128, 128, 0, st>>>(prev, nullptr, offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
+        msm_accumulate_kernel<C, F><<<(nthreads_r + 127) / 128, 128, 0, st>>>(prev, nullptr, offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last, 0u);
     } else
-    msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, 0, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first, s.frag_last);
+    {
+        // measured at 2^20 (gpurun_out/r2_b20_*.json): G1 2.356 vs 2.372 ms with the bulk-staged slab, G2 7.157 vs 7.098 ms
+        // -> on for G1, off for G2; B2G_ACC_BULK=0 / 1 forces it off / on for both
+        static const char* bulk_env = getenv("B2G_ACC_BULK");
+        const bool bulk = bulk_env && *bulk_env ? *bulk_env == '1' : !plan.g2;
+        const uint32_t slab_words = bulk && (size_t)chunk * 128 * 4 <= 48 * 1024 ? chunk * 128u : 0u;
+        msm_accumulate_kernel<C, F><<<(nthreads + 127) / 128, 128, (size_t)slab_words * 4, st>>>(plan.table, sorted.entries, sorted.offsets, nb, chunk, s.buckets, s.frag_first,
+                                                                                                  s.frag_last, slab_words);
+    }
     if (s.prof1) CUDA_CHECK(cudaEventRecord(s.prof1, st));
     cudaStream_t main_st = st;
     if (s.tail) { CUDA_CHECK(cudaEventRecord(s.ev_acc, st)); CUDA_CHECK(cudaStreamWaitEvent(s.tail, s.ev_acc, 0)); st = s.tail; }
