@@ -86,16 +86,40 @@ __device__ __forceinline__ int32_t msm_digit_at(const uint32_t* __restrict__ k, 
     return (int32_t)coef - (int32_t)(cout << c);
 }
 
-// (1b) one thread per (window, scalar): bucket histogram.  Lanes of a warp that hit the same bucket (circom witnesses:
-// most wires are 0/1) are aggregated with match.any so that the hot buckets see one atomic per warp, not 32.
+// (1b) one thread per (window, scalar): bucket histogram.  Hot buckets (circom witnesses: most wires are 0 / 1, so one bucket
+// receives a large share of all entries) must not cost one atomic per entry, but match.any - the general way to group equal
+// lanes - was the kernel's main stall on uniform scalars (short-scoreboard 14.6 per issue, L2 at 48 %).  Two leader rounds do:
+// the first pending lane broadcasts its bucket, every lane with the same bucket is counted by ONE atomic; a hot bucket is the
+// leader's with high probability, and on uniform data the rounds cost four ballots.  Lanes still pending add individually.
+constexpr int MSM_LEADER_ROUNDS = 2;
+
 __global__ void __launch_bounds__(256) msm_count_kernel(const fe* __restrict__ canon, uint32_t n, int c, int nwin, uint32_t* __restrict__ counts) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t w = (uint32_t)(tid / n), i = (uint32_t)(tid % n);
     int32_t d = 0;
     if (w < (uint32_t)nwin) d = msm_digit_at(canon[i].l, c, (int)w);
     const uint32_t b = d ? (uint32_t)(d < 0 ? -d : d) - 1u : 0xffffffffu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, b);
-    if (d != 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&counts[b], (uint32_t)__popc(peers));
+    const uint32_t lane = threadIdx.x & 31;
+    bool pending = d != 0;
+    {   // bucket 0 (digit +-1) is where the bits of a circom witness land: always grouped, one ballot
+        const uint32_t hot = __ballot_sync(0xffffffffu, pending && b == 0u);
+        if (hot) {
+            if ((int)lane == __ffs(hot) - 1) atomicAdd(&counts[0], (uint32_t)__popc(hot));
+            if (b == 0u) pending = false;
+        }
+    }
+    #pragma unroll
+    for (int round = 0; round < MSM_LEADER_ROUNDS; round++) {
+        const uint32_t pend = __ballot_sync(0xffffffffu, pending);
+        if (!pend) break;
+        const int leader = __ffs(pend) - 1;
+        const uint32_t lb = __shfl_sync(0xffffffffu, b, leader);
+        const bool mine = pending && b == lb;
+        const uint32_t same = __ballot_sync(0xffffffffu, mine);
+        if ((int)lane == leader) atomicAdd(&counts[lb], (uint32_t)__popc(same));
+        if (mine) pending = false;
+    }
+    if (pending) atomicAdd(&counts[b], 1u);
 }
 
 // ------------------------------------------------------------------------------------------------ (2) exclusive scan (one CTA)
@@ -141,15 +165,38 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const fe* __restrict__
     if (w < (uint32_t)nwin) d = msm_digit_at(canon[i].l, c, (int)w);
     const uint32_t b = d ? (uint32_t)(d < 0 ? -d : d) - 1u : 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t peers = __match_any_sync(0xffffffffu, b);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (d != 0 && (int)lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (d != 0) {
-        const uint32_t pos = offsets[b] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        entries[pos] = (w * row_stride + i) | (d < 0 ? 0x80000000u : 0u);
+    const uint32_t entry = (w * row_stride + i) | (d < 0 ? 0x80000000u : 0u);
+    bool pending = d != 0;
+    {   // hot bucket 0 first (see msm_count_kernel)
+        const uint32_t hot = __ballot_sync(0xffffffffu, pending && b == 0u);
+        if (hot) {
+            const int leader = __ffs(hot) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&cursor[0], (uint32_t)__popc(hot));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pending && b == 0u) {
+                entries[offsets[0] + base + (uint32_t)__popc(hot & ((1u << lane) - 1u))] = entry;
+                pending = false;
+            }
+        }
     }
+    #pragma unroll
+    for (int round = 0; round < MSM_LEADER_ROUNDS; round++) {            // same leader rounds as the histogram pass
+        const uint32_t pend = __ballot_sync(0xffffffffu, pending);
+        if (!pend) break;
+        const int leader = __ffs(pend) - 1;
+        const uint32_t lb = __shfl_sync(0xffffffffu, b, leader);
+        const bool mine = pending && b == lb;
+        const uint32_t same = __ballot_sync(0xffffffffu, mine);
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(&cursor[lb], (uint32_t)__popc(same));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mine) {
+            entries[offsets[b] + base + (uint32_t)__popc(same & ((1u << lane) - 1u))] = entry;
+            pending = false;
+        }
+    }
+    if (pending) entries[offsets[b] + atomicAdd(&cursor[b], 1u)] = entry;
 }
 
 // ------------------------------------------------------------------------------------------------ (4a) batched-affine pre-reduction
