@@ -63,13 +63,18 @@ struct MsmScratch {                      // one per in-flight MSM
     void *aff_pref = nullptr, *aff_totals = nullptr, *aff_tscratch = nullptr;
 };
 
+// Window size by base count, from whole-proof measurements on B200 (round 2: gpurun_out/r2_b25_*, r2_b26_*, r2_shard_sweep*.log;
+// round 1 for >= 0.8 M).  Larger windows than the textbook log2(n) - 3 pay off below 2^19 because the table removes the
+// per-window reductions: 2^14 keys 740 -> 970 proofs/s (c 11 -> 13), 2^16 457 -> 474 (13 -> 15), one rank of an 8-way sharded 2^20
+// proof 8.8 -> 7.9 ms (14 -> 15).  B2G_MSM_C overrides (8..22) for tuning.
 inline int msm_pick_c(uint32_t n) {
+    if (n >= 3u << 18) return 17;        // 15 windows instead of 16 pay for the doubled bucket set from ~0.8 M bases up (18 already loses)
+    if (n >= 1u << 19) return 16;
+    if (n >= 1u << 15) return 15;
+    if (n >= 1u << 13) return 13;
+    if (n >= 1u << 11) return 11;
     int lg = 0; while ((1ull << (lg + 1)) <= n) lg++;
-    int c = lg - 3;
-    if (c < 8) c = 8;
-    if (c > 16) c = 16;
-    if (n >= 3u << 18) c = 17;           // 15 windows instead of 16 pay for the doubled bucket set from ~0.8 M bases up (measured;
-    return c;                            // 18 already loses to the bucket reduction).  B2G_MSM_C overrides (8..22) for tuning
+    return lg - 3 < 8 ? 8 : lg - 3;
 }
 inline int msm_nwin(int c) { return (255 + c - 1) / c; }
 
