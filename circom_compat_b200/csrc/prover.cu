@@ -58,7 +58,6 @@ struct b2g_ctx {
     bool use_graph = true;
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};             // [0] whole proof, [1] sharded proof with the peer-memory exchange
     uint64_t g_key[2][3] = {};                                  // (key uid, matrices uid, buffer generation) each graph was captured for
-    uint64_t debug_uploaded = 0;
     uint64_t alloc_gen = 1;                                    // bumped whenever a buffer the graphs point into is (re)allocated
     uint64_t g_launches[2] = {0, 0};
     unsigned long long* d_epoch = nullptr;                     // exchange epoch (device-resident so that it survives graph replay)
@@ -1008,13 +1007,10 @@ static void prove_common(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, const void* w_m
     ensure_scratch(ctx, pk);
     cudaStream_t s0 = ctx->st[0];
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[12], s0));
-    static const bool skip_upload = getenv("B2G_DEBUG_NO_H2D") != nullptr;      // diagnosis only: reuse the resident witness
     // a rank that takes no part in the split witness map needs only the scalars of its own base range
     size_t first = 0, count = mat->n_vars;
     if (slice_only && map_is_split(ctx, mat) && ctx->shard_rank >= MAP_RANKS) { first = (size_t)pk->scalar_off[Q_A] + pk->lo[Q_A]; count = pk->cnt[Q_A]; }
-    if ((!skip_upload || ctx->debug_uploaded != mat->uid) && count)
-        CUDA_CHECK(cudaMemcpyAsync(ctx->d_w + first, (const uint8_t*)w_mont + first * 32, count * 32, cudaMemcpyHostToDevice, s0));
-    ctx->debug_uploaded = mat->uid;
+    if (count) CUDA_CHECK(cudaMemcpyAsync(ctx->d_w + first, (const uint8_t*)w_mont + first * 32, count * 32, cudaMemcpyHostToDevice, s0));
     CUDA_CHECK(cudaEventRecord(ctx->ev_t[13], s0));
 }
 
