@@ -251,7 +251,12 @@ void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark) {
     d.pass_sb[d.npass] = 0; d.pass_k[d.npass] = d.tl; d.npass++;
     int rem = logn - d.tl;
     if (rem > 0) {
-        int np = (rem + d.tl - 1) / d.tl, sb = d.tl;
+        // index bits per strided pass: 10 = as few passes as possible (1024 x 1 tiles at 2^20); B2G_NTT_MAXK=5 / 6 makes the
+        // outer tiles 2-D (32 x 32 / 64 x 16: coalesced rows) at the price of more global round trips - measured, DESIGN.md section 8
+        int maxk = d.tl;
+        if (const char* e = getenv("B2G_NTT_MAXK")) { int v = atoi(e); if (v >= 1 && v <= d.tl) maxk = v; }
+        int np = (rem + maxk - 1) / maxk, sb = d.tl;
+        if (np > 3) np = 3;                         // pass_sb / pass_k hold four entries
         for (int p = 0; p < np; p++) {
             int k = rem / (np - p);                 // even split
             d.pass_sb[d.npass] = sb; d.pass_k[d.npass] = k; d.npass++;
