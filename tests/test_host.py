@@ -195,6 +195,26 @@ def test_product_verifiers_python_and_cpp(golden, test_zkey_bytes):
     assert e != verifier.F12_ONE and verifier.f12_pow(e, o.R_MOD) == verifier.F12_ONE
 
 
+def test_product_verifier_degenerate_points(test_zkey_bytes):
+    """Points at infinity in a proof: e(inf, Q) = e(P, inf) = 1 (arkworks' multi_miller_loop skips them); such a proof only
+    verifies if the remaining equation holds, which it does not for a real key; both mirrors agree with the oracle."""
+    import subprocess
+    from circom_compat_b200 import Groth16, Proof, read_zkey, verifier
+    pk, _ = read_zkey(test_zkey_bytes)
+    z = o.read_zkey(test_zkey_bytes)
+    pvk = Groth16.process_vk(pk)
+    zero = Proof(bytes(256))
+    assert not Groth16.verify_with_processed_vk(pvk, [33], zero)
+    assert not o.verify(z, [33], (None, None, None))
+    out = subprocess.check_output([HOST_BIN, '--verify', os.path.join(ROOT, 'tests', 'golden', 'test.zkey'), zero.data.hex(), '33'], text=True)
+    assert 'verified=0' in out
+    # pairing with infinity is the identity of GT
+    assert verifier.pairing(None, z.beta_g2) == verifier.F12_ONE and verifier.pairing(z.alpha_g1, None) == verifier.F12_ONE
+    # e(-P, Q) * e(P, Q) = 1
+    e1 = verifier.miller_loop([(z.alpha_g1, z.beta_g2), (verifier.g1_neg(z.alpha_g1), z.beta_g2)])
+    assert verifier.final_exponentiation(e1) == verifier.F12_ONE
+
+
 def test_product_verifier_reference_bench_key(golden, complex_zkey_bytes):
     # benches/groth16.rs:63-66: the proof of the 10 000-constraint chain verifies with inputs = full_assignment[1..num_inputs]
     from circom_compat_b200 import Groth16, Proof, read_zkey
