@@ -213,6 +213,142 @@ __global__ void __launch_bounds__(512, 2) ntt_pass_kernel(NttPassArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ radix-8 register passes
+// [r2] Same butterflies, same twiddles, same results as ntt_pass_kernel above, reorganised so that the multiplier pipe is
+// not waiting on shared memory and barriers: a thread keeps EIGHT elements in registers and runs up to three consecutive
+// stages on them (a radix-8 "round") before the tile is exchanged through shared memory - 3-4 exchanges per pass instead
+// of 10 barrier-separated stages, 1/3 of the shared-memory traffic, and the four twiddle loads of a step are in flight
+// together.  Index bits: the thread's elements differ in a 3-bit field [f, f+3) of the tile-local index; a round on the
+// stage bits [qa, qb) uses f = min(qa, tl-3).  Code size: every step pairs register POSITIONS (p, p+4); between steps the
+// positions are rotated (x_new[p] = x_old[rotl3(p)], 64 register moves on the idle ALU pipe) so that ONE inlined copy of
+// the four butterflies serves all three stage bits.  Position p holds field value rotl3^k(p).  Shared-memory index
+// loc ^ (loc >> 3): conflict-free for every field position (tools/ntt8_model.py checks the schedule and the swizzle on CPU).
+__device__ __forceinline__ uint32_t ntt8_sw(uint32_t loc) { return loc ^ (loc >> 3); }
+__device__ __forceinline__ uint32_t ntt8_rotl3(uint32_t p) { return ((p << 1) | (p >> 2)) & 7u; }
+__device__ __forceinline__ uint32_t ntt8_elem(uint32_t p, int k) {
+    if (k >= 1) p = ntt8_rotl3(p);
+    if (k == 2) p = ntt8_rotl3(p);
+    return p;
+}
+__device__ __forceinline__ uint32_t ntt8_loc(uint32_t tid, uint32_t e, int f) {
+    return ((tid >> f) << (f + 3)) | (e << f) | (tid & ((1u << f) - 1u));
+}
+// bring the position map to rotl3^want (k, want in {0,1,2})
+__device__ __forceinline__ void ntt8_rotate_to(fe (&x)[8], int& k, int want) {
+    const int d = (want - k + 3) % 3;
+    if (d == 1) {            // x_new[p] = x_old[rotl3(p)] : 1<-2<-4<-1, 3<-6<-5<-3
+        fe t = x[1]; x[1] = x[2]; x[2] = x[4]; x[4] = t;
+        t = x[3]; x[3] = x[6]; x[6] = x[5]; x[5] = t;
+    } else if (d == 2) {     // x_new[p] = x_old[rotr3(p)] : 1<-4<-2<-1, 3<-5<-6<-3
+        fe t = x[1]; x[1] = x[4]; x[4] = x[2]; x[2] = t;
+        t = x[3]; x[3] = x[5]; x[5] = x[6]; x[6] = t;
+    }
+    k = want;
+}
+__device__ __forceinline__ void ntt8_exchange(uint32_t* sm, uint32_t tile, uint32_t tid, fe (&x)[8], int f, int nf) {
+    __syncthreads();                                           // everyone has read the previous exchange
+    #pragma unroll
+    for (int p = 0; p < 8; p++) sm_put(sm, tile, ntt8_sw(ntt8_loc(tid, p, f)), x[p]);
+    __syncthreads();
+    #pragma unroll
+    for (int p = 0; p < 8; p++) x[p] = sm_get(sm, tile, ntt8_sw(ntt8_loc(tid, p, nf)));
+}
+
+template <bool POINTWISE>
+__global__ void __launch_bounds__(256, 2) ntt_pass8_kernel(NttPassArgs A) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const uint32_t tile = 1u << A.tl, tid = threadIdx.x;
+    const int cols_log = A.tl - A.k, ftop = A.tl - 3;
+    const uint32_t n = 1u << A.logn;
+    const int nv = POINTWISE ? 3 : 1;
+    for (int vi = 0; vi < nv; vi++) {
+        fe* vec = POINTWISE ? A.vec[vi] : A.vec[blockIdx.y];
+        fe x[8];
+        int f = A.do_dif ? ftop : (cols_log < ftop ? cols_log : ftop), k = 0;
+        #pragma unroll
+        for (int p = 0; p < 8; p++) x[p] = fe_load(&vec[tile_global_index(ntt8_loc(tid, p, f), blockIdx.x, cols_log, A.sb, A.k)]);
+        if (A.do_dif) {
+            for (int qb = A.tl; qb > cols_log;) {
+                const int qa = qb - 3 > cols_log ? qb - 3 : cols_log;
+                const int nf = qa < ftop ? qa : ftop;
+                if (nf != f) { ntt8_exchange(sm, tile, tid, x, f, nf); f = nf; }
+                #pragma unroll 1
+                for (int q = qb - 1; q >= qa; q--) {
+                    ntt8_rotate_to(x, k, (q - f + 1) % 3);
+                    const int s = A.sb + (q - cols_log);                 // global stage: span 2^s
+                    #pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const uint32_t gi = tile_global_index(ntt8_loc(tid, ntt8_elem(p, k), f), blockIdx.x, cols_log, A.sb, A.k);
+                        const uint32_t e2 = (gi & ((1u << s) - 1u)) << (A.logn - s);
+                        const fe u = x[p], v = x[p + 4];
+                        x[p] = Fr::add(u, v);
+                        if (e2 == 0) x[p + 4] = Fr::sub(u, v);
+                        else x[p + 4] = Fr::mul(Fr::sub(v, u), fe_load_nc(&A.tw[n - e2]));   // omega_n^-e = -omega_2n^(n-2e)
+                    }
+                }
+                ntt8_rotate_to(x, k, 0);
+                qb = qa;
+            }
+        }
+        if (A.do_scale) {
+            // position g holds coefficient bitrev(g): multiply by n^-1 * g^bitrev(g)   (qap.rs:63-70)
+            #pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                #pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t g = tile_global_index(ntt8_loc(tid, p + 4 * h, f), blockIdx.x, cols_log, A.sb, A.k);
+                    x[p] = Fr::mul(x[p], fe_load_nc(&A.ct[A.logn ? __brev(g) >> (32 - A.logn) : 0u]));
+                }
+                #pragma unroll
+                for (int p = 0; p < 4; p++) { const fe t = x[p]; x[p] = x[p + 4]; x[p + 4] = t; }
+            }
+        }
+        if (A.do_dit) {
+            for (int qa = cols_log; qa < A.tl;) {
+                const int qb = qa + 3 < A.tl ? qa + 3 : A.tl;
+                const int nf = qa < ftop ? qa : ftop;
+                if (nf != f) { ntt8_exchange(sm, tile, tid, x, f, nf); f = nf; }
+                #pragma unroll 1
+                for (int q = qa; q < qb; q++) {
+                    ntt8_rotate_to(x, k, (q - f + 1) % 3);
+                    const int s = A.sb + (q - cols_log);
+                    #pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const uint32_t gi = tile_global_index(ntt8_loc(tid, ntt8_elem(p, k), f), blockIdx.x, cols_log, A.sb, A.k);
+                        const uint32_t e2 = (gi & ((1u << s) - 1u)) << (A.logn - s);
+                        const fe u = x[p];
+                        fe v = x[p + 4];
+                        if (e2 != 0) v = Fr::mul(v, fe_load_nc(&A.tw[e2]));
+                        x[p] = Fr::add(u, v);
+                        x[p + 4] = Fr::sub(u, v);
+                    }
+                }
+                ntt8_rotate_to(x, k, 0);
+                qa = qb;
+            }
+        }
+        // results: in place, or folded into h = a*b - c (qap.rs:75-85) with `out` as the running value (each thread re-reads
+        // only what it wrote itself; out may alias vec[0])
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            #pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const uint32_t g = tile_global_index(ntt8_loc(tid, p + 4 * h, f), blockIdx.x, cols_log, A.sb, A.k);
+                if (!POINTWISE) fe_store(&vec[g], x[p]);
+                else if (vi == 0) fe_store(&A.out[g], x[p]);
+                else if (vi == 1) fe_store(&A.out[g], Fr::mul(fe_load(&A.out[g]), x[p]));
+                else {
+                    fe r = Fr::sub(fe_load(&A.out[g]), x[p]);
+                    if (A.pw_scale) r = Fr::mul(r, *A.pw_scale);
+                    fe_store(&A.out[g], r);
+                }
+            }
+            #pragma unroll
+            for (int p = 0; p < 4; p++) { const fe t = x[p]; x[p] = x[p + 4]; x[p + 4] = t; }
+        }
+    }
+}
+
 // out[bitrev(i)] = in[i] * (scale ? *scale : 1)
 __global__ void __launch_bounds__(256) bitrev_copy_kernel(const fe* __restrict__ in, fe* __restrict__ out, int logn, const fe* __restrict__ scale,
                                                           const fe* __restrict__ table) {
@@ -245,13 +381,24 @@ void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark) {
         ntt_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logn, d.zinv + 36, d.pw + 30, d.cginv);
     }
     CUDA_CHECK(cudaGetLastError());
-    // pass schedule: block pass (bits [0, tl)), then strided passes over the remaining bits, split evenly
-    d.tl = logn < 10 ? logn : 10;
+    // pass schedule: block pass (bits [0, tl)), then strided passes over the remaining bits, split evenly.
+    // [r2] radix-8 register passes (ntt_pass8_kernel) from 2^5 up; B2G_NTT_RADIX2=1 keeps the one-stage-per-barrier kernel.
+    // Tiles: 1024 elements (128 threads); 2^21 and 2^22 take 2048-element tiles so that they stay at two passes (11 + 10 / 11 + 11).
+    const char* r2 = getenv("B2G_NTT_RADIX2");
+    d.radix8 = logn >= 5 && !(r2 && atoi(r2));
+    int tlmax = 10;
+    if (d.radix8) {
+        if (logn == 21 || logn == 22) tlmax = 11;
+        if (const char* e = getenv("B2G_NTT_TL")) { int v = atoi(e); if (v >= 5 && v <= 11) tlmax = v; }
+        CUDA_CHECK(cudaFuncSetAttribute(ntt_pass8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(ntt_pass8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    }
+    d.tl = logn < tlmax ? logn : tlmax;
     d.npass = 0;
-    d.pass_sb[d.npass] = 0; d.pass_k[d.npass] = d.tl; d.npass++;
+    d.pass_sb[d.npass] = 0; d.pass_k[d.npass] = d.tl; d.pass_tl[d.npass] = d.tl; d.npass++;
     int rem = logn - d.tl;
     if (rem > 0) {
-        // index bits per strided pass: 10 = as few passes as possible (1024 x 1 tiles at 2^20); B2G_NTT_MAXK=5 / 6 makes the
+        // index bits per strided pass: as few passes as possible by default (1024 x 1 tiles at 2^20); B2G_NTT_MAXK=5 / 6 makes the
         // outer tiles 2-D (32 x 32 / 64 x 16: coalesced rows) at the price of more global round trips - measured, DESIGN.md section 8
         int maxk = d.tl;
         if (const char* e = getenv("B2G_NTT_MAXK")) { int v = atoi(e); if (v >= 1 && v <= d.tl) maxk = v; }
@@ -259,7 +406,9 @@ void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark) {
         if (np > 3) np = 3;                         // pass_sb / pass_k hold four entries
         for (int p = 0; p < np; p++) {
             int k = rem / (np - p);                 // even split
-            d.pass_sb[d.npass] = sb; d.pass_k[d.npass] = k; d.npass++;
+            int tl = d.tl;
+            if (d.radix8) { tl = k > 10 ? k : 10; if (tl > logn) tl = logn; }
+            d.pass_sb[d.npass] = sb; d.pass_k[d.npass] = k; d.pass_tl[d.npass] = tl; d.npass++;
             sb += k; rem -= k;
         }
     }
@@ -279,14 +428,19 @@ static void launch_pass(const NttDomain& d, fe* v0, fe* v1, fe* v2, int nvec, fe
                         cudaStream_t st, const fe* coset_table = nullptr, const fe* pw_scale = nullptr) {
     NttPassArgs A;
     A.vec[0] = v0; A.vec[1] = v1; A.vec[2] = v2; A.out = out; A.tw = d.tw; A.ct = coset_table ? coset_table : d.ct; A.pw_scale = pw_scale;
-    A.logn = d.logn; A.tl = d.tl; A.sb = d.pass_sb[pass]; A.k = d.pass_k[pass];
+    A.logn = d.logn; A.tl = d.pass_tl[pass]; A.sb = d.pass_sb[pass]; A.k = d.pass_k[pass];
     A.do_dif = dif; A.do_scale = scale; A.do_dit = dit; A.pointwise = pointwise;
-    const uint32_t tile = 1u << d.tl;
-    const uint32_t ntiles = (uint32_t)(((size_t)1 << d.logn) >> d.tl);
+    const uint32_t tile = 1u << A.tl;
+    const uint32_t ntiles = (uint32_t)(((size_t)1 << d.logn) >> A.tl);
     dim3 grid(ntiles, pointwise ? 1 : nvec);
-    uint32_t threads = tile / 2 ? tile / 2 : 1;
-    if (pointwise) ntt_pass_kernel<true><<<grid, threads, tile * 32, st>>>(A);
-    else ntt_pass_kernel<false><<<grid, threads, tile * 32, st>>>(A);
+    if (d.radix8) {
+        if (pointwise) ntt_pass8_kernel<true><<<grid, tile / 8, tile * 32, st>>>(A);
+        else ntt_pass8_kernel<false><<<grid, tile / 8, tile * 32, st>>>(A);
+    } else {
+        uint32_t threads = tile / 2 ? tile / 2 : 1;
+        if (pointwise) ntt_pass_kernel<true><<<grid, threads, tile * 32, st>>>(A);
+        else ntt_pass_kernel<false><<<grid, threads, tile * 32, st>>>(A);
+    }
     g_launch_count += 1;
 }
 

@@ -8,7 +8,8 @@ namespace b2g {
 
 struct NttDomain {
     int logn = -1, tl = 0, npass = 0;
-    int pass_sb[4] = {0, 0, 0, 0}, pass_k[4] = {0, 0, 0, 0};
+    int pass_sb[4] = {0, 0, 0, 0}, pass_k[4] = {0, 0, 0, 0}, pass_tl[4] = {0, 0, 0, 0};
+    bool radix8 = false;                                      // ntt_pass8_kernel (register radix-8 rounds) instead of ntt_pass_kernel
     fe *tw = nullptr, *ct = nullptr, *pw = nullptr;
     // LibsnarkReduction only: coset by the field generator g = 5 (ark-poly get_coset(F::GENERATOR))
     fe *cg = nullptr, *cginv = nullptr, *zinv = nullptr;      // n^-1 g^k, n^-1 g^-k (k < n), (g^n - 1)^-1

@@ -111,9 +111,9 @@ def test_fixed_base(ctx):
 
 
 # ------------------------------------------------------------------------------------------------ NTT
-# 21 / 22: the >= 2^21 pass schedule (three strided pass definitions instead of two, ntt.cu ntt_domain_create) that the
-# 2^22 configuration (BASELINE.json config 4) runs
-@pytest.mark.parametrize('log_n', [1, 2, 3, 7, 10, 11, 14, 16, 20, 21, 22])
+# 21 / 22: the >= 2^21 pass schedule (2048-element tiles, 11 + 10 / 11 + 11 index bits, ntt.cu ntt_domain_create) that the
+# 2^22 configuration (BASELINE.json config 4) runs; 1..4 run the one-stage-per-barrier kernel, 5 and up the radix-8 register rounds
+@pytest.mark.parametrize('log_n', [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 20, 21, 22])
 def test_ntt_plain(ctx, log_n):
     rng = np.random.default_rng(log_n)
     n = 1 << log_n
@@ -121,6 +121,45 @@ def test_ntt_plain(ctx, log_n):
     vals = c.fr_mul(vals, vals[::-1].copy())                                                 # spread over the field
     assert np.array_equal(ctx.ntt(vals), c.ntt(vals))
     assert np.array_equal(ctx.ntt(vals, inverse=True), c.ntt(vals, inverse=True))
+
+
+# every pass shape of ntt_domain_create: the radix-2 kernel (B2G_NTT_RADIX2=1), small tiles (many strided passes, partial
+# rounds), 2-D strided tiles (B2G_NTT_MAXK), 512- and 2048-element tiles at sizes where they are not the default
+@pytest.mark.parametrize('env', [dict(B2G_NTT_RADIX2='1'), dict(B2G_NTT_TL='5'), dict(B2G_NTT_TL='6', B2G_NTT_MAXK='2'),
+                                 dict(B2G_NTT_TL='7', B2G_NTT_MAXK='4'), dict(B2G_NTT_TL='9'), dict(B2G_NTT_TL='11'),
+                                 dict(B2G_NTT_MAXK='5'), dict(B2G_NTT_RADIX2='1', B2G_NTT_MAXK='5')],
+                         ids=lambda e: ','.join('%s=%s' % (k[8:], v) for k, v in e.items()))
+@pytest.mark.parametrize('log_n', [9, 13, 17])
+def test_ntt_pass_schedules(ctx, monkeypatch, env, log_n):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(1000 + log_n)
+    n = 1 << log_n
+    vals = c.fr_to_mont(c.ints_to_limbs([int(x) for x in rng.integers(0, 2**62, n)]))
+    vals = c.fr_mul(vals, vals[::-1].copy())
+    assert np.array_equal(ctx.ntt(vals), c.ntt(vals))
+    assert np.array_equal(ctx.ntt(vals, inverse=True), c.ntt(vals, inverse=True))
+
+
+@pytest.mark.parametrize('env', [dict(B2G_NTT_RADIX2='1'), dict(B2G_NTT_TL='6', B2G_NTT_MAXK='3'), dict(B2G_NTT_TL='11'), dict(B2G_NTT_MAXK='5')],
+                         ids=lambda e: ','.join('%s=%s' % (k[8:], v) for k, v in e.items()))
+def test_witness_map_pass_schedules(ctx, monkeypatch, env):
+    # the fused chain (DIF passes, DIF + coset scale + DIT block pass, DIT passes + h = a*b - c) under every pass shape,
+    # CircomReduction and LibsnarkReduction, against oracle/cref.c
+    from circom_compat_b200 import CircomReduction, LibsnarkReduction, fr_to_mont, synth, release
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    log_n = 13
+    circ = synth.chain_circuit(1 << log_n); w = synth.chain_witness(1 << log_n)
+    wm = fr_to_mont(w)
+    cm = circ.matrices()
+    h = CircomReduction.witness_map_from_matrices(cm, circ.num_inputs, circ.num_constraints, wm, ctx)
+    assert np.array_equal(h, c.witness_map(cm.num_constraints, circ.num_inputs, circ.n_vars, cm.a, cm.b, wm))
+    release(cm)
+    cm3 = circ.matrices(with_c=True)
+    h = LibsnarkReduction.witness_map_from_matrices(cm3, circ.num_inputs, circ.num_constraints, wm, ctx)
+    assert np.array_equal(h, c.witness_map_libsnark(cm3.num_constraints, cm3.num_instance_variables, cm3.a, cm3.b, cm3.c, wm))
+    release(cm3)
 
 
 def test_ntt_linearity_large(ctx):

@@ -391,3 +391,14 @@ def test_truncated_and_corrupt_files_fail_cleanly(tmp_path, test_zkey_bytes):
     for cut in (2, 30, 60):
         with pytest.raises(Exception):
             read_wtns(wtns[:cut])
+
+
+def test_ntt8_index_model():
+    """The register/shared-memory schedule of ntt_pass8_kernel, modelled on the CPU (tools/ntt8_model.py): forward transform ==
+    DFT definition, inverse round trip, and the fused evaluations-on-H -> evaluations-on-gH chain, for one-pass, two-pass,
+    three-pass and 2-D-tile schedules (small tiles stand in for the 1024/2048-element ones)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ntt8_model', os.path.join(os.path.dirname(__file__), '..', 'tools', 'ntt8_model.py'))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    for log_n, tlmax, maxk in [(3, 3, None), (5, 5, None), (7, 7, None), (7, 4, None), (8, 4, None), (9, 5, None), (10, 4, None), (9, 5, 2), (10, 6, 3), (11, 6, None)]:
+        m.check(log_n, tlmax, maxk)
