@@ -923,6 +923,13 @@ int b2g_pk_free(b2g_pk* pk) {
     });
 }
 
+static void mat_release(b2g_mat* mat) {
+    ntt_domain_destroy(mat->dom);
+    for (void* p : {(void*)mat->a_rowptr, (void*)mat->a_col, (void*)mat->b_rowptr, (void*)mat->b_col, (void*)mat->a_val, (void*)mat->b_val,
+                    (void*)mat->c_rowptr, (void*)mat->c_col, (void*)mat->c_val}) if (p) cudaFree(p);
+    delete mat;
+}
+
 int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
     return guarded([&] {
         if (!ctx || !d || !out) throw_error(B2G_E_SHAPE, "null pointer");
@@ -953,6 +960,7 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
         DevGuard g(ctx->device);
         cudaStream_t st = ctx->st[0];
         b2g_mat* mat = new b2g_mat();
+        struct MatGuard { b2g_mat* m; ~MatGuard() { if (m) { cudaDeviceSynchronize(); mat_release(m); } } } guard{mat};   // a failed upload or table build frees everything
         mat->device = ctx->device; mat->m = m; mat->num_inputs = d->num_inputs; mat->n_vars = d->n_vars; mat->logn = logn; mat->n = 1u << logn;
         mat->a_rowptr = dev_upload<uint32_t>(d->a_rowptr, ((size_t)m + 1) * 4, st);
         mat->b_rowptr = dev_upload<uint32_t>(d->b_rowptr, ((size_t)m + 1) * 4, st);
@@ -969,6 +977,7 @@ int b2g_matrices_load(b2g_ctx* ctx, const b2g_mat_desc* d, b2g_mat** out) {
         ntt_domain_create(mat->dom, logn, st, libsnark);
         g_launch_count += 2;
         CUDA_CHECK(cudaStreamSynchronize(st));
+        guard.m = nullptr;
         *out = mat;
     });
 }
@@ -978,10 +987,7 @@ int b2g_matrices_free(b2g_mat* mat) {
         if (!mat) return;
         DevGuard g(mat->device);
         cudaDeviceSynchronize();
-        ntt_domain_destroy(mat->dom);
-        for (void* p : {(void*)mat->a_rowptr, (void*)mat->a_col, (void*)mat->b_rowptr, (void*)mat->b_col, (void*)mat->a_val, (void*)mat->b_val,
-                        (void*)mat->c_rowptr, (void*)mat->c_col, (void*)mat->c_val}) if (p) cudaFree(p);
-        delete mat;
+        mat_release(mat);
     });
 }
 
