@@ -383,12 +383,11 @@ void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark) {
     CUDA_CHECK(cudaGetLastError());
     // pass schedule: block pass (bits [0, tl)), then strided passes over the remaining bits, split evenly.
     // [r2] radix-8 register passes (ntt_pass8_kernel) from 2^5 up; B2G_NTT_RADIX2=1 keeps the one-stage-per-barrier kernel.
-    // Tiles: 1024 elements (128 threads); 2^21 and 2^22 take 2048-element tiles so that they stay at two passes (11 + 10 / 11 + 11).
+    // Tiles: 1024 elements (128 threads; B2G_NTT_TL = 5..11 overrides, 2048 elements = 256 threads).
     const char* r2 = getenv("B2G_NTT_RADIX2");
     d.radix8 = logn >= 5 && !(r2 && atoi(r2));
     int tlmax = 10;
     if (d.radix8) {
-        if (logn == 21 || logn == 22) tlmax = 11;
         if (const char* e = getenv("B2G_NTT_TL")) { int v = atoi(e); if (v >= 5 && v <= 11) tlmax = v; }
         CUDA_CHECK(cudaFuncSetAttribute(ntt_pass8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CUDA_CHECK(cudaFuncSetAttribute(ntt_pass8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -398,9 +397,12 @@ void ntt_domain_create(NttDomain& d, int logn, cudaStream_t st, bool libsnark) {
     d.pass_sb[d.npass] = 0; d.pass_k[d.npass] = d.tl; d.pass_tl[d.npass] = d.tl; d.npass++;
     int rem = logn - d.tl;
     if (rem > 0) {
-        // index bits per strided pass: as few passes as possible by default (1024 x 1 tiles at 2^20); B2G_NTT_MAXK=5 / 6 makes the
-        // outer tiles 2-D (32 x 32 / 64 x 16: coalesced rows) at the price of more global round trips - measured, DESIGN.md section 8
-        int maxk = d.tl;
+        // index bits per strided pass.  Up to 2^20 the three vectors (96 MB) live in the 126 MB L2, 32-byte strided accesses cost
+        // nothing extra and the fewest passes win (1024 x 1 tiles; B2G_NTT_MAXK=5 / 6 = 2-D tiles measured equal).
+        // From 2^21 on the passes stream from DRAM, where single 32-byte sectors at a 64 KB stride run at a fraction of the
+        // bandwidth: strided tiles become 2-D with rows of >= 8 consecutive elements (256 B), i.e. <= 7 index bits per pass
+        // (measured at 2^22: witness map 12.2 ms with 11 + 11 bits on 2048 x 1 tiles vs 6.8 ms with 10 + 6 + 6).
+        int maxk = logn > 20 && d.tl > 7 ? 7 : d.tl;
         if (const char* e = getenv("B2G_NTT_MAXK")) { int v = atoi(e); if (v >= 1 && v <= d.tl) maxk = v; }
         int np = (rem + maxk - 1) / maxk, sb = d.tl;
         if (np > 3) np = 3;                         // pass_sb / pass_k hold four entries

@@ -111,7 +111,7 @@ def test_fixed_base(ctx):
 
 
 # ------------------------------------------------------------------------------------------------ NTT
-# 21 / 22: the >= 2^21 pass schedule (2048-element tiles, 11 + 10 / 11 + 11 index bits, ntt.cu ntt_domain_create) that the
+# 21 / 22: the >= 2^21 pass schedule (block pass + two 2-D strided passes of <= 7 index bits, ntt.cu ntt_domain_create) that the
 # 2^22 configuration (BASELINE.json config 4) runs; 1..4 run the one-stage-per-barrier kernel, 5 and up the radix-8 register rounds
 @pytest.mark.parametrize('log_n', [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 20, 21, 22])
 def test_ntt_plain(ctx, log_n):
