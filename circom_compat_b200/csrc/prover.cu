@@ -557,7 +557,17 @@ static void check_shapes(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat) {
 
 // device part of a proof up to the five partial MSM results (witness must already be in ctx->d_w).
 // The four witness-scalar queries (L, A, B1, B2) are defined over the same index range and share ONE digit sort.
-static const int WITNESS_ORDER[4] = {Q_B2, Q_A, Q_B1, Q_L};     // the G2 MSM is the longest: start it first
+// Launch order of the four witness MSMs.  Each is a GPU-filling accumulation followed by a latency chain on a few CTAs (fold,
+// bucket reduction, and for A / B1 the scalar multiplication by s / r: ~1.3 ms together, ~0.9 ms for B2, ~0.45 ms for L).  The
+// chains with the longest tails go first so that their tails run under the accumulations that follow: A, B1, B2, L.  On one GPU
+// at 2^20 the order is immaterial (16.6 ms of accumulation hides every tail); for one shard of an 8-way sharded proof the
+// accumulations are 0.3 / 0.3 / 0.9 / 0.3 ms and the order decides which tail sticks out.  B2G_MSM_ORDER=b2 restores B2-first.
+static const int WITNESS_ORDER_TAILS[4] = {Q_A, Q_B1, Q_B2, Q_L};
+static const int WITNESS_ORDER_B2[4] = {Q_B2, Q_A, Q_B1, Q_L};
+static const int* witness_order() {
+    const char* e = getenv("B2G_MSM_ORDER");
+    return (e && e[0] == 'b' && e[1] == '2') ? WITNESS_ORDER_B2 : WITNESS_ORDER_TAILS;
+}
 
 // scale: also compute s*msm_A and r*msm_B1 (d_rs must hold r, s) on those MSMs' own streams, right behind them
 static unsigned long long p2p_timeout_ns() {
@@ -606,7 +616,9 @@ static void launch_msms(b2g_ctx* ctx, b2g_pk* pk, b2g_mat* mat, bool timed, bool
         msm_sort(pk->plan[Q_B1], ctx->scratch[Q_B1], ctx->d_wb, pk->b_compact, true, sb);
         CUDA_CHECK(cudaEventRecord(ctx->ev_sortb, sb));
     }
-    for (int q : WITNESS_ORDER) {
+    const int* order = witness_order();
+    for (int oi = 0; oi < 4; oi++) {
+        const int q = order[oi];
         const bool on_b = bsparse && (q == Q_B1 || q == Q_B2);
         if (on_b) { if (q != Q_B1) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sortb, 0)); }
         else if (q != Q_L) CUDA_CHECK(cudaStreamWaitEvent(ctx->st[q], ctx->ev_sort, 0));
