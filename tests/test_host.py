@@ -400,5 +400,6 @@ def test_ntt8_index_model():
     import importlib.util
     spec = importlib.util.spec_from_file_location('ntt8_model', os.path.join(os.path.dirname(__file__), '..', 'tools', 'ntt8_model.py'))
     m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
-    for log_n, tlmax, maxk in [(3, 3, None), (5, 5, None), (7, 7, None), (7, 4, None), (8, 4, None), (9, 5, None), (10, 4, None), (9, 5, 2), (10, 6, 3), (11, 6, None)]:
+    for log_n, tlmax, maxk in [(3, 3, None), (5, 5, None), (7, 7, None), (7, 4, None), (8, 4, None), (9, 5, None), (10, 4, None), (9, 5, 2), (10, 6, 3), (11, 6, None),
+                              (10, 10, None), (11, 11, None), (12, 10, None), (13, 10, 7)]:   # the real 1024- and 2048-element tiles
         m.check(log_n, tlmax, maxk)
