@@ -356,6 +356,7 @@ typedef Reduction<B2G_REDUCTION_LIBSNARK> LibsnarkReduction;   // ark-groth16's 
 
 }  // namespace ark_circom
 #include "ark_circom_verifier.hpp"
+#include "ark_circom_ethereum.hpp"
 namespace ark_circom {
 
 template <class QAP = CircomReduction>

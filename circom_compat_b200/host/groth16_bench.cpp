@@ -3,6 +3,7 @@
 //
 //   groth16_bench --parse-only <circuit.zkey> [--dump-key]         host-only: print what read_zkey produced (no GPU)
 //   groth16_bench --verify <circuit.zkey> <proof_hex> [inputs...]  host-only: process_vk + verify_with_processed_vk
+//   groth16_bench --ethereum <circuit.zkey> <proof_hex> [inputs...] host-only: src/ethereum.rs views of vk / proof / inputs, both directions
 //   groth16_bench <circuit.zkey> chain:<a>|<witness.wtns> [iters] [r_hex s_hex]
 //       chain:<a> = the witness of the reference's squaring-chain bench family for input a
 //       (test-vectors/complex-circuit/input.json has a = 3), computed on the host instead of by WASM.
@@ -93,6 +94,43 @@ int main(int argc, char** argv) {
             for (int i = 4; i < argc; i++) { std::string a = argv[i]; inputs.push_back(a.rfind("0x", 0) == 0 ? Fr::from_bigint(parse_hex(a)) : Fr::from_u64(std::stoull(a))); }
             auto pvk = Groth16::process_vk(kv.first.vk);                    // src/zkey.rs:868
             std::printf("verified=%d\n", Groth16::verify_with_processed_vk(pvk, inputs, proof) ? 1 : 0);
+            return 0;
+        }
+        if (argc >= 4 && std::string(argv[1]) == "--ethereum") {            // host-only: the Ethereum views (src/ethereum.rs) and their way back
+            namespace eth = ark_circom::ethereum;
+            std::ifstream f(argv[2], std::ios::binary);
+            if (!f) throw SerializationError("cannot open zkey");
+            auto kv = read_zkey(f);
+            std::string hx = argv[3];
+            if (hx.size() != 512) throw std::invalid_argument("proof must be 256 bytes of hex");
+            Proof proof;
+            for (int i = 0; i < 256; i++) proof.bytes[i] = (uint8_t)std::stoul(hx.substr(2 * i, 2), nullptr, 16);
+            std::vector<Fr> inputs;
+            for (int i = 4; i < argc; i++) { std::string a = argv[i]; inputs.push_back(a.rfind("0x", 0) == 0 ? Fr::from_bigint(parse_hex(a)) : Fr::from_u64(std::stoull(a))); }
+            const eth::VerifyingKey evk = eth::VerifyingKey::from(kv.first.vk);
+            const eth::Proof ep = eth::Proof::from(proof);
+            auto g1s = [](const eth::G1& g) { auto t = g.as_tuple(); return t[0].hex() + "," + t[1].hex(); };
+            auto g2s = [](const eth::G2& g) { auto t = g.as_tuple(); return t[0][0].hex() + "," + t[0][1].hex() + "," + t[1][0].hex() + "," + t[1][1].hex(); };
+            std::printf("vk.alpha1=%s\nvk.beta2=%s\nvk.gamma2=%s\nvk.delta2=%s\n", g1s(evk.alpha1).c_str(), g2s(evk.beta2).c_str(), g2s(evk.gamma2).c_str(), g2s(evk.delta2).c_str());
+            for (size_t i = 0; i < evk.ic.size(); i++) std::printf("vk.ic[%zu]=%s\n", i, g1s(evk.ic[i]).c_str());
+            std::printf("proof.a=%s\nproof.b=%s\nproof.c=%s\ncalldata=", g1s(ep.a).c_str(), g2s(ep.b).c_str(), g1s(ep.c).c_str());
+            for (const eth::U256& w : ep.calldata_words()) std::printf("%s", w.hex().c_str());
+            std::printf("\n");
+            const std::vector<eth::U256> ein = eth::inputs(inputs);
+            for (size_t i = 0; i < ein.size(); i++) std::printf("inputs[%zu]=%s\n", i, ein[i].hex().c_str());
+            // the reference's convert_vk / convert_proof / convert_fr tests (src/ethereum.rs:195-279), then check_proof with the host verifier
+            const VerifyingKey vk2 = evk.into();
+            bool rt = !memcmp(&vk2.alpha_g1, &kv.first.vk.alpha_g1, 64) && !memcmp(&vk2.beta_g2, &kv.first.vk.beta_g2, 128) &&
+                      !memcmp(&vk2.gamma_g2, &kv.first.vk.gamma_g2, 128) && !memcmp(&vk2.delta_g2, &kv.first.vk.delta_g2, 128) &&
+                      vk2.gamma_abc_g1.size() == kv.first.vk.gamma_abc_g1.size();
+            for (size_t i = 0; rt && i < vk2.gamma_abc_g1.size(); i++) rt = !memcmp(&vk2.gamma_abc_g1[i], &kv.first.vk.gamma_abc_g1[i], 64);
+            const Proof p2 = ep.into();
+            rt = rt && !memcmp(p2.bytes, proof.bytes, 256) && eth::Proof::from(p2) == ep;
+            std::vector<Fr> in2;
+            for (const eth::U256& w : ein) in2.push_back(eth::u256_to_fr(w));
+            for (size_t i = 0; i < inputs.size(); i++) rt = rt && in2[i] == inputs[i];
+            std::printf("roundtrip=%d\n", rt ? 1 : 0);
+            std::printf("verified=%d\n", Groth16::verify_with_processed_vk(Groth16::process_vk(vk2), in2, p2) ? 1 : 0);
             return 0;
         }
         if (argc < 3) { std::fprintf(stderr, "usage: %s [--parse-only] <zkey> chain:<a>|<wtns> [iters] [r_hex s_hex]\n", argv[0]); return 2; }
