@@ -46,6 +46,20 @@ def deser_key_kat(src):
     return out
 
 
+def field_constant_kats():
+    """The scalar-field constants the reference's own sources hold as literals, by regex:
+    r as the hex string its witness-calculator test asserts (src/witness/witness_calculator.rs:328-332), R^-1 mod r as the
+    decimal it hard-codes (src/witness/memory.rs:45-48; R = 2^256), r as the little-endian bytes its .r1cs reader accepts
+    (src/circom/r1cs_reader.rs:180-182)."""
+    wc = open(os.path.join(REF, 'src/witness/witness_calculator.rs')).read()
+    mem = open(os.path.join(REF, 'src/witness/memory.rs')).read()
+    r1 = open(os.path.join(REF, 'src/circom/r1cs_reader.rs')).read()
+    r_hex = re.search(r'wtns\.prime\.to_str_radix\(16\),\s*"([0-9A-Fa-f]{64})"', wc).group(1).lower()
+    r_inv = re.search(r'let r_inv = BigInt::from_str\(\s*"(\d+)"', mem).group(1)
+    r_le = re.search(r'hex::decode\("([0-9a-f]{64})"\)', r1).group(1)
+    return {'r_hex': r_hex, 'r_inv_dec': r_inv, 'r_le_hex': r_le}
+
+
 def main():
     out = {'r': str(R), 's': str(S)}
     src = open(os.path.join(REF, 'src/zkey.rs')).read()
@@ -53,6 +67,8 @@ def main():
     out['kat_fq_one'] = rust_byte_vec(src, 'fq_buf')
     out['kat_g1_one'] = rust_byte_vec(src, 'g1_buf')
     out['kat_g2_one'] = rust_byte_vec(src, 'g2_buf')
+
+    out['field_constants'] = field_constant_kats()
 
     z = o.read_zkey(open(os.path.join(HERE, 'test.zkey'), 'rb').read())
     w = [1, 33, 3, 11]                                   # test-vectors/mycircuit-witness.json

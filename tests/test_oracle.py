@@ -180,3 +180,26 @@ def test_msm_truncates_to_shorter_side():
 def test_witness_map_domain_too_large():
     with pytest.raises(ValueError):
         o.domain_size_for((1 << 28) + 1)
+
+
+def test_field_constants_held_by_the_reference(golden):
+    """r as the hex string the reference's witness-calculator test asserts (src/witness/witness_calculator.rs:328-332), R^-1 mod r
+    as the decimal literal of src/witness/memory.rs:45-48 and r as the little-endian bytes its .r1cs reader insists on
+    (src/circom/r1cs_reader.rs:180-182), extracted by tests/golden/make_golden.py: the oracle's and the product's scalar-field
+    modulus and Montgomery radix are these."""
+    from circom_compat_b200 import fr_to_mont, fr_from_mont
+    from circom_compat_b200.zkey import R_MOD
+    k = golden['field_constants']
+    r = int(k['r_hex'], 16)
+    assert r == o.R_MOD == R_MOD
+    assert int.from_bytes(bytes.fromhex(k['r_le_hex']), 'little') == r
+    r_inv = int(k['r_inv_dec'])
+    assert r_inv == pow(1 << 256, -1, r)
+    # the Montgomery form used on the wire (zkey coefficients, witnesses, the C ABI) is x * 2^256 mod r: x_mont * R^-1 = x
+    xs = [1, 2, 33, r - 1, 0x1234567890abcdef1234567890abcdef]
+    mont = fr_to_mont(xs)
+    for x, limbs in zip(xs, mont):
+        m = sum(int(v) << (64 * i) for i, v in enumerate(limbs))
+        assert m == (x << 256) % r and m * r_inv % r == x
+    assert [int(v) for v in fr_from_mont(mont)] == xs
+    assert np.array_equal(c.fr_to_mont(c.ints_to_limbs(xs)), mont)
