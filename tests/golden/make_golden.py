@@ -60,6 +60,24 @@ def field_constant_kats():
     return {'r_hex': r_hex, 'r_inv_dec': r_inv, 'r_le_hex': r_le}
 
 
+def witness_kats():
+    """The witnesses the reference's witness-calculator tests expect (src/witness/witness_calculator.rs:260-311): multiplier_1/2/3
+    (inputs test-vectors/mycircuit-input{1,2,3}.json on mycircuit.r1cs; 2 and 3 wrap around the field) by regex from the test
+    source, and safe_multipler = test-vectors/safe-circuit-witness.json (circuit2, 132 wires).  Witness GENERATION is out of scope
+    here; these vectors are reference-pinned INPUTS of the proving path and known-answers for the .r1cs / .wtns readers."""
+    src = open(os.path.join(REF, 'src/witness/witness_calculator.rs')).read()
+    mult = []
+    for k in (1, 2, 3):
+        body = re.search(r'async fn multiplier_%d\(\) \{(.*?)\n    \}\n' % k, src, re.S).group(1)
+        wit = re.search(r'witness: &\[(.*?)\]', body, re.S).group(1)
+        mult.append(re.findall(r'"(\d+)"', wit))
+        assert len(mult[-1]) == 4
+    inputs = [json.load(open(os.path.join(REF, 'test-vectors/mycircuit-input%d.json' % k))) for k in (1, 2, 3)]
+    safe = json.load(open(os.path.join(REF, 'test-vectors/safe-circuit-witness.json')))
+    return {'multiplier': mult, 'multiplier_inputs': [{k: str(v) for k, v in i.items()} for i in inputs], 'safe_multiplier': safe,
+            'mycircuit_witness_json': json.load(open(os.path.join(REF, 'test-vectors/mycircuit-witness.json')))}
+
+
 def main():
     out = {'r': str(R), 's': str(S)}
     src = open(os.path.join(REF, 'src/zkey.rs')).read()
@@ -69,6 +87,7 @@ def main():
     out['kat_g2_one'] = rust_byte_vec(src, 'g2_buf')
 
     out['field_constants'] = field_constant_kats()
+    out['witness_kats'] = witness_kats()
 
     z = o.read_zkey(open(os.path.join(HERE, 'test.zkey'), 'rb').read())
     w = [1, 33, 3, 11]                                   # test-vectors/mycircuit-witness.json

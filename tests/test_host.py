@@ -481,3 +481,31 @@ def test_cpp_ethereum_views_match_python(golden):
     # a coordinate that is not a canonical Fq element cannot come back (u256_to_point's expect in the reference)
     r = subprocess.run([HOST_BIN, '--ethereum', zk, 'ff' * 256, '33'], capture_output=True, text=True)
     assert r.returncode == 1 and 'canonical' in r.stderr
+
+
+def test_reference_witness_kats_through_the_builder(golden):
+    """The four witnesses the reference's witness-calculator tests pin (src/witness/witness_calculator.rs:260-311: multiplier_1/2/3 on
+    mycircuit, safe_multipler on circuit2; two of them wrap around the field) fed through the builder mirror: each satisfies its
+    .r1cs (read by the product's reader), yields the public inputs circuit.rs:18-26 defines, and the snarkjs witness.wtns fixture
+    equals the reference-held JSON element for element - a known answer for read_wtns that does not come from this repository."""
+    from circom_compat_b200 import CircomConfig, CircomBuilder, read_wtns
+    from circom_compat_b200.zkey import R_MOD
+    g = os.path.join(ROOT, 'tests', 'golden')
+    k = golden['witness_kats']
+    assert k['mycircuit_witness_json'] == k['multiplier'][0] == ['1', '33', '3', '11']
+    for wit, inp in zip(k['multiplier'], k['multiplier_inputs']):
+        wit = [int(x) for x in wit]
+        a, b = int(inp['a']), int(inp['b'])
+        assert wit == [1, a * b % R_MOD, a % R_MOD, b]                       # c <== a * b, reduced mod r by the calculator
+        builder = CircomBuilder.new(CircomConfig.new(lambda inputs, wit=wit: wit, os.path.join(g, 'mycircuit.r1cs')))
+        builder.push_input('a', a); builder.push_input('b', b)
+        circom = builder.build()                                            # raises on an unsatisfied constraint
+        assert circom.witness == wit and circom.get_public_inputs() == [wit[1]]
+    safe = [int(x) for x in k['safe_multiplier']]
+    assert len(safe) == 132
+    assert read_wtns(open(os.path.join(g, 'circuit2_witness.wtns'), 'rb').read()) == safe
+    c2 = CircomBuilder.new(CircomConfig.new(lambda inputs: safe, os.path.join(g, 'circuit2.r1cs'))).build()
+    assert c2.get_public_inputs() == [33]
+    tampered = list(safe); tampered[5] = (tampered[5] + 1) % R_MOD
+    with pytest.raises(ValueError):
+        CircomBuilder.new(CircomConfig.new(lambda inputs: tampered, os.path.join(g, 'circuit2.r1cs'))).build()
