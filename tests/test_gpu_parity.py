@@ -313,24 +313,6 @@ def test_witness_map_and_proofs_test_zkey(ctx, golden, test_zkey_bytes):
             assert o.verify(z, w[1:cm.num_instance_variables], (p.a, p.b, p.c))
 
 
-def test_proofs_of_the_reference_witness_kats(ctx, golden, test_zkey_bytes):
-    """The witnesses the reference's witness-calculator tests pin for mycircuit (src/witness/witness_calculator.rs:260-298:
-    multiplier_1/2/3; 2 and 3 carry scalars a few units below r) proved with the reference's test.zkey: proof bytes equal the
-    big-int oracle's and verify against the public input circuit.rs:18-26 derives from the witness."""
-    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont
-    pk, cm = read_zkey(test_zkey_bytes)
-    z = o.read_zkey(test_zkey_bytes)
-    r, s = int(golden['r']), int(golden['s'])
-    pvk = Groth16.process_vk(pk)
-    for wit in golden['witness_kats']['multiplier']:
-        w = [int(x) for x in wit]
-        p = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont(w), ctx)
-        A, B, C = o.prove(z, r, s, w)
-        assert p.data == o.proof_to_bytes(A, B, C)
-        assert Groth16.verify_with_processed_vk(pvk, w[1:cm.num_instance_variables], p)
-        assert not Groth16.verify_with_processed_vk(pvk, [(w[1] + 1) % o.R_MOD], p)
-
-
 def test_witness_map_and_proof_complex_zkey(ctx, golden, complex_zkey_bytes):
     # the reference's bench workload (benches/groth16.rs:13-85): 10 000-constraint chain, domain 2^14
     from circom_compat_b200 import read_zkey, Groth16, CircomReduction, fr_to_mont
@@ -879,3 +861,21 @@ def test_edge_ragged_rows_and_repeated_columns(ctx):
     for r_, c_, v in zip(rows_b, cols_b, vals_b): B[r_].append((v, c_))
     assert c.limbs_to_ints(c.fr_from_mont(h)) == o.witness_map_from_matrices(A, B, li, m, w)
     release(cm)
+
+
+def test_proofs_of_the_reference_witness_kats(ctx, golden, test_zkey_bytes):
+    """The witnesses the reference's witness-calculator tests pin for mycircuit (src/witness/witness_calculator.rs:260-298:
+    multiplier_1/2/3; 2 and 3 carry scalars a few units below r) proved with the reference's test.zkey: proof bytes equal the
+    big-int oracle's and verify against the public input circuit.rs:18-26 derives from the witness."""
+    from circom_compat_b200 import read_zkey, Groth16, fr_to_mont
+    pk, cm = read_zkey(test_zkey_bytes)
+    z = o.read_zkey(test_zkey_bytes)
+    r, s = int(golden['r']), int(golden['s'])
+    pvk = Groth16.process_vk(pk)
+    for wit in golden['witness_kats']['multiplier']:
+        w = [int(x) for x in wit]
+        p = Groth16.create_proof_with_reduction_and_matrices(pk, r, s, cm, cm.num_instance_variables, cm.num_constraints, fr_to_mont(w), ctx)
+        A, B, C = o.prove(z, r, s, w)
+        assert p.data == o.proof_to_bytes(A, B, C)
+        assert Groth16.verify_with_processed_vk(pvk, w[1:cm.num_instance_variables], p)
+        assert not Groth16.verify_with_processed_vk(pvk, [(w[1] + 1) % o.R_MOD], p)
